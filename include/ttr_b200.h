@@ -1,0 +1,198 @@
+/* ttr_b200.h — C ABI of libttr_b200.so: the sm_100a (B200) hot path of
+ * jpe17/TwoTowerMLRetrieval (GRU two-tower encode, triplet step, exact cosine top-k,
+ * hybrid rerank).
+ *
+ * The reference is pure Python/PyTorch and has no FFI of its own; each entry point below
+ * names the reference call site it replaces (file:line in the reference tree).  The
+ * binding a maintainer adds on the reference side is a ctypes stub — see INTEGRATION.md.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer owned by the caller unless the name ends in `_h`;
+ *    the library never allocates or frees caller-visible memory;
+ *  - `stream` is a cudaStream_t passed as void*; calls are stream-ordered and never
+ *    synchronise unless documented;
+ *  - return value: 0 = OK, non-zero = error; ttr_last_error() gives the thread-local text;
+ *  - no CPU fallback: on a machine without an sm_100 device every compute call fails.
+ */
+#ifndef TTR_B200_H
+#define TTR_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TTR_OK 0
+#define TTR_ERR_INVALID 1
+#define TTR_ERR_CUDA 2
+#define TTR_ERR_UNSUPPORTED 3
+
+const char* ttr_last_error(void);
+int ttr_version(void);
+/* Number of SMs of the current device (grid sizing on the host side). */
+int ttr_sm_count(int* out_h);
+
+/* ---- sequence plan -------------------------------------------------------------------
+ * Replaces `lengths = (x != 0).sum(dim=1).cpu()` + `pack_padded_sequence(enforce_sorted=
+ * False)` (backend/model.py:52-57) without the device->host sync.
+ * ids      int64 [B, T] right-padded with 0 (collate layout, backend/main.py:50-56)
+ * lengths  int32 [B]     count_nonzero per row (quirk #1: the first `length` positions are
+ *                        the sequence)
+ * order    int32 [B]     sorted position -> row, lengths non-increasing
+ * offsets  int32 [B+1]   token offset of each sorted position in the packed layout;
+ *                        offsets[B] = total tokens
+ * status   int32 [4]     [0] number of zero-length rows (reference raises RuntimeError),
+ *                        [1] total tokens, [2] max length, [3] reserved
+ * Requires T <= 8192. */
+int ttr_seq_plan(const int64_t* ids, int B, int T, int32_t* lengths, int32_t* order,
+                 int32_t* offsets, int32_t* status, void* stream);
+
+/* ---- K1: embedding gather --------------------------------------------------------------
+ * Replaces `self.embedding(x)` (backend/model.py:49).  Writes the packed token matrix
+ * X[offsets[s] + t, 0:E] = table[ids[order[s], t], 0:E] for t < length.  `round_tf32` != 0
+ * rounds to TF32 (round-to-nearest) because X only feeds the tensor-core projection. */
+int ttr_embed_gather(const int64_t* ids, int B, int T, const float* table, int64_t V, int E,
+                     const int32_t* order, const int32_t* offsets, float* X, int round_tf32,
+                     void* stream);
+
+/* ---- K3: GRU input projection ----------------------------------------------------------
+ * Replaces the `X W_ih^T + b_ih` half of `self.rnn(packed)` (backend/model.py:59-62) for
+ * all timesteps and both directions at once: C[M, N] = A[M, K] * W[N, K]^T + bias[N].
+ * tcgen05 (kind::tf32, fp32 accumulate in TMEM) + TMA.  The number of valid rows is read
+ * on the device from *m_valid (may be NULL = m_bound); m_bound sizes the grid.
+ * Requirements: K % 4 == 0, N % 8 == 0, A/W/C 16-byte aligned. */
+int ttr_gemm_tf32_bias(const float* A, const float* W, const float* bias, float* C,
+                       int m_bound, const int32_t* m_valid, int N, int K, void* stream);
+/* Same contract, plain fp32 CUDA-core kernel.  Test-only reference for the tcgen05 path. */
+int ttr_debug_gemm_fp32_bias(const float* A, const float* W, const float* bias, float* C,
+                             int m_bound, const int32_t* m_valid, int N, int K, void* stream);
+/* C[N, K] (+)= A[M, N]^T * Bm[M, K] over the valid rows: the weight-gradient contraction
+ * dW = dG^T X of the GRU backward (autograd of backend/main.py:254).  fp32 split-K. */
+int ttr_gemm_tn_fp32(const float* A, const float* Bm, float* C, int m_bound,
+                     const int32_t* m_valid, int N, int K, int accumulate, void* stream);
+/* C[M, K] = A[M, N] * W[N, K]  (dX = dG W_ih), tcgen05 tf32 is not needed for parity of
+ * gradients; fp32 CUDA cores. */
+int ttr_gemm_nn_fp32(const float* A, const float* W, float* C, int m_bound,
+                     const int32_t* m_valid, int N, int K, int accumulate, void* stream);
+
+/* ---- K4: GRU recurrence ----------------------------------------------------------------
+ * Replaces the sequential half of `self.rnn(packed)` (backend/model.py:59-62), one layer,
+ * all directions.  gate order r,z,n; h0 = 0; per-row final state captured at each row's own
+ * last step (forward) / after position 0 (reverse).
+ * gi      fp32 [Mtok, dirs*3H]  input projections incl. b_ih (from ttr_gemm_*_bias)
+ * w_hh    fp32 [dirs, 3H, H];  b_hh fp32 [dirs, 3H]
+ * y       fp32 [Mtok, dirs*H]   per-step outputs (NULL if not needed)
+ * h_last  fp32 [B, dirs*H]      final states in ORIGINAL row order
+ * saved   fp32 [Mtok, dirs, 4, H] (r, z, n, W_hn h + b_hn) for the backward pass, or NULL
+ * H == 256 runs the register-resident 8-CTA-cluster kernel; other H use a generic kernel. */
+int ttr_gru_recurrence_fwd(const float* gi, const float* w_hh, const float* b_hh,
+                           const int32_t* order, const int32_t* offsets, int B, int H, int dirs,
+                           float* y, float* h_last, float* saved, void* stream);
+/* BPTT of one layer.  In: dy [Mtok, dirs*H] (grad wrt per-step outputs, NULL = zero),
+ * dh_last [B, dirs*H] (grad wrt final states, original row order, NULL = zero), y (this
+ * layer's forward outputs), saved.  Out: dgi [Mtok, dirs*3H] (grad wrt gi, also the b_ih
+ * gradient rows) and dgh [Mtok, dirs*3H] (grad wrt W_hh h + b_hh). */
+int ttr_gru_recurrence_bwd(const float* dy, const float* dh_last, const float* y,
+                           const float* saved, const float* w_hh, const int32_t* order,
+                           const int32_t* offsets, int B, int H, int dirs, float* dgi, float* dgh,
+                           void* stream);
+/* dW_hh[dir] (+)= dgh[:, dir]^T h_prev[:, dir], where h_prev is y shifted by one step inside
+ * each row (0 at a row's first step).  hprev_ws: scratch fp32 [m_bound, dirs*H].
+ * Out: dw_hh [dirs, 3H, H].  (Bias gradients are column sums: ttr_colsum.) */
+int ttr_gru_whh_grad(const float* dgh, const float* y, const int32_t* offsets, int B, int H,
+                     int dirs, int m_bound, float* hprev_ws, float* dw_hh, int accumulate,
+                     void* stream);
+/* Embedding gradient for a trainable table (pretrained_embeddings=None, backend/model.py:24-27):
+ * dtable[ids] += dX over the packed tokens; id 0 (padding_idx) gets none. */
+int ttr_embed_scatter_grad(const int64_t* ids, int B, int T, int64_t V, int E,
+                           const int32_t* order, const int32_t* offsets, const float* dX,
+                           float* dtable, void* stream);
+/* out[N] (+)= column sums of A[m_valid, N] (b_ih / b_hh / projection-bias gradients). */
+int ttr_colsum(const float* A, int m_bound, const int32_t* m_valid, int N, float* out,
+               int accumulate, void* stream);
+/* Test/debug switches: bit0 = force the generic (any-H) GRU kernels, bit1 = encode TMA maps
+ * as FLOAT32 instead of TFLOAT32. */
+int ttr_debug_set_flags(int flags);
+
+/* ---- K5/K6: projection + L2 normalise --------------------------------------------------
+ * Replaces `cat(h_n[-2], h_n[-1])` -> `self.projection` -> `F.normalize(p=2, dim=1)`
+ * (backend/model.py:65-74).  h_cat [B, IN]; w [H, IN] or NULL (unidirectional: IN == H, no
+ * projection); raw_out [B, H] pre-normalisation values (NULL unless training);
+ * normalize != 0 applies v / max(||v||, 1e-12). */
+int ttr_proj_l2norm_fwd(const float* h_cat, const float* w, const float* bias, int B, int IN,
+                        int H, int normalize, float* out, float* raw_out, void* stream);
+/* Backward of the normalise: d_raw = d(out)/d(raw)^T d_out.  The projection's own backward is
+ * two small GEMMs (ttr_gemm_nn_fp32 / ttr_gemm_tn_fp32) plus ttr_colsum. */
+int ttr_l2norm_bwd(const float* d_out, const float* raw, int B, int H, int normalize,
+                   float* d_raw, void* stream);
+
+/* ---- K7: cosine triplet loss -----------------------------------------------------------
+ * Replaces `triplet_loss_cosine` (backend/model.py:109-114): loss = mean(max(0, cos(q,n) -
+ * cos(q,p) + margin)), F.cosine_similarity eps 1e-8.  loss_out fp32 [1]; the backward
+ * writes dq, dp, dn = d loss / d inputs times *dloss (device scalar, NULL = 1). */
+int ttr_triplet_fwd(const float* q, const float* p, const float* n, int B, int H, float margin,
+                    float* loss_out, void* stream);
+int ttr_triplet_bwd(const float* q, const float* p, const float* n, int B, int H, float margin,
+                    const float* dloss, float* dq, float* dp, float* dn, void* stream);
+/* `TwoTowerTrainer.compute_batch_metrics` (backend/trainer.py:38-55): out fp32 [5] =
+ * accuracy, similarity_gap, magnitude, pos_similarity, neg_similarity. */
+int ttr_batch_metrics(const float* q, const float* p, const float* n, int B, int H, float* out,
+                      void* stream);
+
+/* ---- K9/K10: clip_grad_norm_ + Adam ----------------------------------------------------
+ * Replaces `clip_grad_norm_(params, max_norm)` + `optimizer.step()` (backend/main.py:257-259)
+ * over one flat fp32 bucket.  grad_scale multiplies the gradients first (1/world after an
+ * all-reduce sum).  max_norm <= 0 disables clipping (backend/trainer.py:101-110 variant).
+ * norm_out fp32 [1] receives the pre-clip total norm.  step is 1-based. */
+int ttr_clip_adam(float* params, const float* grads, float* exp_avg, float* exp_avg_sq,
+                  int64_t n, float grad_scale, float max_norm, float lr, float beta1, float beta2,
+                  float eps, int step, float* norm_out, float* workspace /* >= 1024 floats */,
+                  void* stream);
+
+/* ---- K11/K12: exact cosine top-k -------------------------------------------------------
+ * Replaces `torch.matmul(q, D.t())` + `torch.topk(sim, k)` (backend/evaluators.py:185-186,
+ * :50/:62, :269-272; backend/trainer.py:62-65) and ChromaDB's ANN `collection.query(
+ * n_results=50)` (frontend/main.py:153-156) with an exact fused scan that never
+ * materialises [B, N].
+ * Q fp32 [B, D]; docs fp32 [N, D] row-major (the document_embeddings.npy layout,
+ * backend/main.py:138); D must be 256 for the fused kernels; k <= 64.
+ * row_offset is added to the emitted indices (global ids of a row shard).
+ * out_scores fp32 [B, k] descending; out_idx int64 [B, k]; ties: lower index first.
+ * workspace: ttr_score_topk_workspace_bytes(B, N, k) bytes. */
+int64_t ttr_score_topk_workspace_bytes(int B, int64_t N, int k);
+int ttr_score_topk(const float* Q, int B, const float* docs, int64_t N, int D, int k,
+                   int64_t row_offset, float* out_scores, int64_t* out_idx, void* workspace,
+                   int64_t workspace_bytes, void* stream);
+/* Merge P candidate lists per query (rank shards after the all-gather, or CTA partials):
+ * cand_scores fp32 [P, B, kin], cand_idx int64 [P, B, kin] -> top-k, same ordering rule. */
+int ttr_topk_merge(const float* cand_scores, const int64_t* cand_idx, int P, int B, int kin,
+                   int k, float* out_scores, int64_t* out_idx, void* stream);
+
+/* ---- K14: hybrid rerank ----------------------------------------------------------------
+ * Replaces frontend/main.py:158-198: semantic = 2*cos-1 (space=0, Chroma default squared-L2)
+ * or cos (space=1); tfidf = <doc TF-IDF row, query TF-IDF row> (L2-normalised CSR rows);
+ * final = alpha*semantic + (1-alpha)*tfidf; stable descending sort; first `top_n`.
+ * cand_idx int64 [B, kc] LOCAL row ids into the CSR (idx - csr_row_offset), cand_cos fp32;
+ * doc CSR: indptr int64, indices int32 (sorted per row), data fp64; query CSR likewise
+ * (q_indptr int64 [B+1]).  tfidf_in: optional fp64 [B, kc] precomputed TF-IDF scores (used
+ * after a cross-rank gather); if NULL they are computed from the CSR.
+ * Outputs (fp64 [B, top_n] each): final, semantic, tfidf; out_pos int32 [B, top_n] = position
+ * in the candidate list. */
+int ttr_hybrid_rerank(const int64_t* cand_idx, const float* cand_cos, int B, int kc,
+                      int64_t csr_row_offset, const int64_t* indptr, const int32_t* indices,
+                      const double* data, const int64_t* q_indptr, const int32_t* q_indices,
+                      const double* q_data, const double* tfidf_in, double alpha, int space,
+                      int top_n, double* out_final, double* out_sem, double* out_tfidf,
+                      int32_t* out_pos, void* stream);
+/* TF-IDF scores only, for candidates owned by this shard (others get 0):
+ * out fp64 [B, kc]. */
+int ttr_tfidf_candidates(const int64_t* cand_idx, int B, int kc, int64_t csr_row_offset,
+                         int64_t csr_rows, const int64_t* indptr, const int32_t* indices,
+                         const double* data, const int64_t* q_indptr, const int32_t* q_indices,
+                         const double* q_data, double* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TTR_B200_H */

@@ -1,0 +1,155 @@
+"""CPU: host-side logic — state_dict/seed compatibility with the reference module, flat
+parameter views, shard bounds, bulk-encode batching, tokenizer, 2-rank gloo merge scheme."""
+import os
+import pickle
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden_weights, load_golden
+from oracle import towers_numpy as onp
+from twotowermlretrieval_b200 import TwoTowerModel, synth
+from twotowermlretrieval_b200.encode import plan_batches
+from twotowermlretrieval_b200.index import shard_bounds
+from twotowermlretrieval_b200.tokenizer import PretrainedTokenizer
+
+REF = Path("/root/reference/backend")
+
+
+def test_state_dict_keys_and_shapes_match_reference_contract():
+    cfg = synth.default_config(vocab_size=300, embed_dim=200)
+    m = TwoTowerModel(cfg)
+    sd = m.state_dict()
+    want = {}
+    for tower in ("query_encoder", "doc_encoder"):
+        for k, shape in synth.tower_param_shapes(cfg).items():
+            want[f"{tower}.{k}"] = shape
+    assert set(sd.keys()) == set(want.keys())
+    for k, shape in want.items():
+        assert tuple(sd[k].shape) == tuple(shape), k
+    n_train = sum(p.numel() for n, p in m.named_parameters() if "embedding" not in n)
+    assert n_train == 4035072          # trainable GRU/projection params of both towers
+
+
+@pytest.mark.skipif(not REF.exists(), reason="reference tree not present (GPU box)")
+def test_same_seed_gives_reference_initialisation_and_loads_both_ways():
+    sys.path.insert(0, str(REF))
+    import model as refmodel
+    cfg = synth.default_config(vocab_size=120, embed_dim=20)
+    cfg["HIDDEN_DIM"] = 24
+    torch.manual_seed(123)
+    ref = refmodel.TwoTowerModel(cfg)
+    torch.manual_seed(123)
+    ours = TwoTowerModel(cfg)
+    rs, os_ = ref.state_dict(), ours.state_dict()
+    assert list(rs.keys()) == list(os_.keys())
+    for k in rs:
+        assert torch.equal(rs[k], os_[k]), k
+    ours.load_state_dict(rs)
+    ref.load_state_dict(ours.state_dict())
+    table = np.random.default_rng(0).standard_normal((120, 20)).astype(np.float32)
+    ours2 = TwoTowerModel(cfg, table)
+    assert not ours2.query_encoder.embedding.weight.requires_grad     # model.py:25-27
+
+
+def test_flat_views_survive_load_and_move():
+    cfg = synth.default_config(vocab_size=60, embed_dim=12)
+    cfg["HIDDEN_DIM"] = 16
+    m = TwoTowerModel(cfg)
+    flat = m.flat_params()
+    sd = {k: torch.randn_like(v) for k, v in m.state_dict().items()}
+    m.load_state_dict(sd)
+    assert m._views_ok()
+    w, b, whh, bhh = m.query_encoder.layer_weights(1)
+    assert torch.equal(w[:48], sd["query_encoder.rnn.weight_ih_l1"])
+    assert torch.equal(w[48:], sd["query_encoder.rnn.weight_ih_l1_reverse"])
+    assert torch.equal(whh[1], sd["query_encoder.rnn.weight_hh_l1_reverse"])
+    assert torch.equal(bhh[48:], sd["query_encoder.rnn.bias_hh_l1_reverse"])
+    m.double().float()                      # _apply re-allocates storage -> lazily re-packed
+    assert m.flat_params().numel() == flat.numel() and m._views_ok()
+    g = m.flat_grads()
+    assert all(p.grad is not None and p.grad.data_ptr() >= g.data_ptr() for n, p in m.named_parameters()
+               if "embedding" not in n)
+
+
+def test_lstm_is_rejected():
+    with pytest.raises(NotImplementedError):
+        TwoTowerModel(dict(synth.default_config(50, 8), RNN_TYPE="LSTM"))
+
+
+def test_shard_bounds_cover_rows_exactly_once():
+    for n in (0, 1, 7, 8, 1000, 8841823):
+        for world in (1, 2, 3, 8):
+            spans = [shard_bounds(n, world, r) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            assert all(hi - lo <= -(-n // world) for lo, hi in spans)
+
+
+def test_plan_batches_is_a_partition_within_budget():
+    rng = np.random.default_rng(0)
+    lengths = synth.make_lengths(5000, "passage", rng)
+    order, bounds = plan_batches(lengths, max_tokens=8192, max_rows=256)
+    assert sorted(order.tolist()) == list(range(5000))
+    assert bounds[0][0] == 0 and bounds[-1][1] == 5000
+    for lo, hi in bounds:
+        T = lengths[order[lo]]
+        assert hi - lo <= 256 and ((hi - lo) * T <= 8192 or hi - lo == 1)
+        assert (lengths[order[lo:hi]] <= T).all()
+
+
+def test_tokenizer_matches_reference_rules(tmp_path):
+    w2i = {"the": 0, "cat": 1, ".": 2, "sat": 3}
+    p = tmp_path / "w.pkl"
+    with open(p, "wb") as f:
+        pickle.dump(w2i, f)
+    tok = PretrainedTokenizer(str(p))
+    assert tok.vocab_size() == 5 and tok.unk_token_id == 4                   # tokenizer.py:20-24
+    assert tok.encode("The CAT sat, on... the mat!") == [0, 1, 3, 4, 4, 2, 2, 2, 0, 4, 4]
+    assert tok.encode("") == [] and tok.decode([1, 3, 99]) == "cat sat <UNK>"
+    if REF.exists():
+        sys.path.insert(0, str(REF))
+        import tokenizer as reftok
+        rt = reftok.PretrainedTokenizer(str(p))
+        for s in ["The CAT sat, on... the mat!", "a_b c-d; e?f", "Ünïcode wörds 123", ""]:
+            assert rt.encode(s) == tok.encode(s)
+    with pytest.raises(FileNotFoundError):
+        PretrainedTokenizer(str(tmp_path / "missing.pkl"))
+
+
+def _gloo_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        D = synth.make_unit_rows(4001, 256, seed=3)
+        Q = synth.make_unit_rows(6, 256, seed=4)
+        lo, hi = shard_bounds(D.shape[0], world, rank)
+        s, i = onp.cosine_topk(Q, D[lo:hi], 50, dtype=np.float32)      # stand-in for the local kernel
+        s, i = torch.tensor(s), torch.tensor(i + lo)
+        gs = [torch.empty_like(s) for _ in range(world)]
+        gi = [torch.empty_like(i) for _ in range(world)]
+        dist.all_gather(gs, s)
+        dist.all_gather(gi, i)
+        cs, ci = torch.cat(gs, 1).numpy(), torch.cat(gi, 1).numpy()
+        order = np.lexsort((ci, -cs), axis=1)[:, :50]
+        ms, mi = np.take_along_axis(cs, order, 1), np.take_along_axis(ci, order, 1)
+        fs, fi = onp.cosine_topk(Q, D, 50, dtype=np.float32)
+        q.put((rank, bool((mi == fi).all()), float(np.abs(ms - fs).max())))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_gloo_shard_gather_merge_equals_global_topk():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    [p.start() for p in procs]
+    res = [q.get(timeout=180) for _ in range(2)]
+    [p.join(60) for p in procs]
+    assert all(ok for _, ok, _ in res) and all(err < 1e-6 for _, _, err in res)

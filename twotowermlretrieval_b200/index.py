@@ -1,0 +1,229 @@
+"""Exact dense retrieval + hybrid rerank on the GPU (additive API).
+
+Replaces the reference's `torch.matmul(q, D.t())` + `torch.topk` call sites
+(`backend/evaluators.py:185-186`, `backend/trainer.py:62-65`), the ChromaDB ANN query of
+the frontend (`frontend/main.py:153-156`) and the Python rerank loop
+(`frontend/main.py:158-198`).  Row shards of the document matrix live on different GPUs;
+the only exchange is an all-gather of the per-rank top-k candidate lists.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+
+SPACE_L2 = 0       # Chroma default: semantic = 1 - ||q-d||^2 = 2cos - 1 (frontend/main.py:162)
+SPACE_COSINE = 1   # semantic = cos
+
+
+def _space_code(space) -> int:
+    if space in (SPACE_L2, "l2"):
+        return SPACE_L2
+    if space in (SPACE_COSINE, "cosine"):
+        return SPACE_COSINE
+    raise ValueError(f"unknown space {space!r} (use 'l2' or 'cosine')")
+
+
+_WORKSPACES: dict = {}
+
+
+def _workspace(nbytes: int, device) -> torch.Tensor:
+    key = (device.index if device.index is not None else torch.cuda.current_device())
+    ws = _WORKSPACES.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(int(nbytes), dtype=torch.uint8, device=device)
+        _WORKSPACES[key] = ws
+    return ws
+
+
+def search_topk(Q: torch.Tensor, docs: torch.Tensor, k: int = 50, row_offset: int = 0,
+                out: Optional[Tuple[torch.Tensor, torch.Tensor]] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Exact top-k of Q @ docs.T per query, without materialising the score matrix.
+
+    Q fp32 [B, 256], docs fp32 [N, 256] (both CUDA, contiguous).  Returns (scores fp32
+    [B, k] descending, idx int64 [B, k] + row_offset); ties: lower index first.  k is
+    clamped to N like the reference's evaluators do implicitly (`k=max(top_k)` on small
+    candidate sets would raise in torch; here missing slots carry -inf / -1)."""
+    _lib.require_cuda(Q, "search_topk(Q)")
+    _lib.require_cuda(docs, "search_topk(docs)")
+    if Q.dim() == 1:
+        Q = Q.unsqueeze(0)
+    Q = Q.contiguous().float()
+    if not docs.is_contiguous() or docs.dtype != torch.float32:
+        raise _lib.TTRError("search_topk: docs must be a contiguous float32 [N, D] matrix")
+    B, D = Q.shape
+    N = docs.shape[0]
+    lib = _lib.load()
+    nbytes = lib.ttr_score_topk_workspace_bytes(B, N, k)
+    ws = _workspace(nbytes, Q.device)
+    if out is None:
+        scores = torch.empty(B, k, dtype=torch.float32, device=Q.device)
+        idx = torch.empty(B, k, dtype=torch.int64, device=Q.device)
+    else:
+        scores, idx = out
+    _lib.call("ttr_score_topk", Q, B, docs, N, D, k, int(row_offset), scores, idx, ws, ws.numel())
+    return scores, idx
+
+
+def topk_merge(cand_scores: torch.Tensor, cand_idx: torch.Tensor, k: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Merge P candidate lists per query: cand_* [P, B, kin] -> (scores [B,k], idx [B,k])."""
+    P, B, kin = cand_scores.shape
+    cand_scores = cand_scores.contiguous()
+    cand_idx = cand_idx.contiguous()
+    scores = torch.empty(B, k, dtype=torch.float32, device=cand_scores.device)
+    idx = torch.empty(B, k, dtype=torch.int64, device=cand_scores.device)
+    _lib.call("ttr_topk_merge", cand_scores, cand_idx, P, B, kin, k, scores, idx)
+    return scores, idx
+
+
+@dataclass
+class CsrF64:
+    """L2-normalised TF-IDF rows on the device (sklearn `TfidfVectorizer` output layout,
+    `backend/main.py:142-143`): indptr int64 [rows+1], indices int32 (sorted per row), data fp64."""
+    indptr: torch.Tensor
+    indices: torch.Tensor
+    data: torch.Tensor
+    rows: int
+    row_offset: int = 0
+
+    @staticmethod
+    def from_arrays(indptr, indices, data, device, row_offset: int = 0) -> "CsrF64":
+        ip = torch.as_tensor(np.asarray(indptr, dtype=np.int64), device=device)
+        ix = torch.as_tensor(np.asarray(indices, dtype=np.int32), device=device)
+        dv = torch.as_tensor(np.asarray(data, dtype=np.float64), device=device)
+        return CsrF64(ip, ix, dv, int(ip.numel() - 1), int(row_offset))
+
+    @staticmethod
+    def from_scipy(mat, device, row_offset: int = 0) -> "CsrF64":
+        mat = mat.tocsr()
+        mat.sort_indices()
+        return CsrF64.from_arrays(mat.indptr, mat.indices, mat.data, device, row_offset)
+
+    def row_slice(self, lo: int, hi: int) -> "CsrF64":
+        """Rows [lo, hi) as an independent CSR (host-side shard split)."""
+        ip = self.indptr[lo:hi + 1]
+        base = int(ip[0])
+        end = int(ip[-1])
+        return CsrF64((ip - base).contiguous(), self.indices[base:end].contiguous(),
+                      self.data[base:end].contiguous(), hi - lo, self.row_offset + lo)
+
+
+def tfidf_candidates(cand_idx: torch.Tensor, docs_csr: CsrF64, q_csr: CsrF64) -> torch.Tensor:
+    """TF-IDF cosine of every candidate this shard owns (0 elsewhere): fp64 [B, kc]."""
+    B, kc = cand_idx.shape
+    out = torch.empty(B, kc, dtype=torch.float64, device=cand_idx.device)
+    _lib.call("ttr_tfidf_candidates", cand_idx.contiguous(), B, kc, docs_csr.row_offset, docs_csr.rows,
+              docs_csr.indptr, docs_csr.indices, docs_csr.data, q_csr.indptr, q_csr.indices, q_csr.data, out)
+    return out
+
+
+def hybrid_rerank(cand_idx: torch.Tensor, cand_cos: torch.Tensor, alpha: float,
+                  docs_csr: Optional[CsrF64] = None, q_csr: Optional[CsrF64] = None,
+                  tfidf: Optional[torch.Tensor] = None, space="l2", top_n: int = 10):
+    """The `/search` rerank (frontend/main.py:158-198) for a batch of queries.
+
+    cand_idx int64 [B, kc] (global document ids, dense-rank order), cand_cos fp32 [B, kc].
+    Either (docs_csr, q_csr) or precomputed `tfidf` fp64 [B, kc] must be given.
+    Returns dict(final, semantic, tfidf fp64 [B, top_n], pos int32 [B, top_n], idx int64 [B, top_n])."""
+    B, kc = cand_idx.shape
+    dev = cand_idx.device
+    cand_idx = cand_idx.contiguous()
+    cand_cos = cand_cos.contiguous().float()
+    fin = torch.empty(B, top_n, dtype=torch.float64, device=dev)
+    sem = torch.empty_like(fin)
+    tf = torch.empty_like(fin)
+    pos = torch.empty(B, top_n, dtype=torch.int32, device=dev)
+    if tfidf is not None:
+        _lib.call("ttr_hybrid_rerank", cand_idx, cand_cos, B, kc, 0, None, None, None, None, None, None,
+                  tfidf.contiguous(), float(alpha), _space_code(space), top_n, fin, sem, tf, pos)
+    else:
+        if docs_csr is None or q_csr is None:
+            raise ValueError("hybrid_rerank needs (docs_csr, q_csr) or tfidf")
+        _lib.call("ttr_hybrid_rerank", cand_idx, cand_cos, B, kc, docs_csr.row_offset, docs_csr.indptr,
+                  docs_csr.indices, docs_csr.data, q_csr.indptr, q_csr.indices, q_csr.data, None,
+                  float(alpha), _space_code(space), top_n, fin, sem, tf, pos)
+    idx = torch.gather(cand_idx, 1, pos.clamp_min(0).long())
+    return {"final": fin, "semantic": sem, "tfidf": tf, "pos": pos, "idx": idx}
+
+
+def shard_bounds(n_rows: int, world: int, rank: int) -> Tuple[int, int]:
+    """Contiguous row shard of rank: rows [r*ceil(N/R), min(N, (r+1)*ceil(N/R)))  (SURVEY §8e)."""
+    per = -(-n_rows // world)
+    lo = min(n_rows, rank * per)
+    return lo, min(n_rows, lo + per)
+
+
+class ShardedIndex:
+    """Row-sharded exact index: each rank keeps `docs_local` fp32 [n_local, 256] resident in HBM.
+
+    `search` = local fused score+top-k -> all-gather of [B,k] (score, global id) over
+    NCCL/NVLink -> merge kernel; the result is identical on every rank and independent of
+    the number of shards.  With `group=None` and world size 1 no collective is issued."""
+
+    def __init__(self, docs_local: torch.Tensor, row_offset: int = 0, n_total: Optional[int] = None,
+                 group=None, tfidf_local: Optional[CsrF64] = None):
+        _lib.require_cuda(docs_local, "ShardedIndex(docs_local)")
+        self.docs = docs_local.contiguous()
+        self.row_offset = int(row_offset)
+        self.n_total = int(n_total if n_total is not None else docs_local.shape[0])
+        self.group = group
+        self.tfidf = tfidf_local
+        import torch.distributed as dist
+        self._dist = dist
+        self.world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+        self.rank = dist.get_rank(group) if self.world > 1 else 0
+
+    def _local(self, Q, k):
+        if self.docs.shape[0] == 0:
+            B = Q.shape[0]
+            return (torch.full((B, k), float("-inf"), device=Q.device),
+                    torch.full((B, k), -1, dtype=torch.int64, device=Q.device))
+        return search_topk(Q, self.docs, k, self.row_offset)
+
+    def search(self, Q: torch.Tensor, k: int = 50):
+        s, i = self._local(Q, k)
+        if self.world == 1:
+            return s, i
+        B = s.shape[0]
+        gs = torch.empty(self.world, B, k, dtype=s.dtype, device=s.device)
+        gi = torch.empty(self.world, B, k, dtype=i.dtype, device=i.device)
+        self._dist.all_gather_into_tensor(gs, s, group=self.group)
+        self._dist.all_gather_into_tensor(gi, i, group=self.group)
+        return topk_merge(gs, gi, k)
+
+    def search_hybrid(self, Q: torch.Tensor, q_csr: CsrF64, alpha: float, k: int = 50, top_n: int = 10,
+                      space="l2"):
+        """Dense top-k -> TF-IDF of the candidates (each rank scores the rows it owns) ->
+        blend -> top_n.  Candidate TF-IDF scores travel with the candidates in the same
+        all-gather, so no rank needs another rank's CSR slice."""
+        if self.tfidf is None:
+            raise ValueError("ShardedIndex was built without a TF-IDF shard")
+        s, i = self._local(Q, k)
+        tf = tfidf_candidates(i, self.tfidf, q_csr)
+        if self.world > 1:
+            B = s.shape[0]
+            gs = torch.empty(self.world, B, k, dtype=s.dtype, device=s.device)
+            gi = torch.empty(self.world, B, k, dtype=i.dtype, device=i.device)
+            gt = torch.empty(self.world, B, k, dtype=tf.dtype, device=tf.device)
+            self._dist.all_gather_into_tensor(gs, s, group=self.group)
+            self._dist.all_gather_into_tensor(gi, i, group=self.group)
+            self._dist.all_gather_into_tensor(gt, tf, group=self.group)
+            # merge on (score, source position): shards are ascending row ranges and each list is
+            # sorted by (score desc, id asc), so source order == id order among equal scores
+            src = torch.arange(self.world * k, device=s.device, dtype=torch.int64).view(self.world, 1, k)
+            src = src.expand(self.world, B, k).contiguous()
+            ms, msrc = topk_merge(gs, src, k)
+            flat_i = gi.permute(1, 0, 2).reshape(B, self.world * k)
+            flat_t = gt.permute(1, 0, 2).reshape(B, self.world * k)
+            valid = msrc >= 0
+            msrc_c = msrc.clamp_min(0)
+            i = torch.where(valid, torch.gather(flat_i, 1, msrc_c), torch.full_like(msrc, -1))
+            tf = torch.where(valid, torch.gather(flat_t, 1, msrc_c), torch.zeros_like(ms, dtype=torch.float64))
+            s = ms
+        out = hybrid_rerank(i, s, alpha, tfidf=tf, space=space, top_n=top_n)
+        out["dense_scores"], out["dense_idx"] = s, i
+        return out
