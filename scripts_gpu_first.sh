@@ -1,0 +1,13 @@
+#!/bin/bash
+# first GPU pass: per-file pytest processes (a faulting kernel only poisons its own process)
+mkdir -p gpurun_out
+nvidia-smi --query-gpu=name,memory.total,clocks.max.sm --format=csv > gpurun_out/gpu.txt 2>&1
+for f in test_gpu_gemm test_gpu_search test_gpu_towers test_gpu_train test_gpu_hybrid; do
+  timeout 900 python -m pytest tests/$f.py -q -m gpu -x --timeout=600 -s > gpurun_out/$f.log 2>&1
+  echo "$f exit $?" >> gpurun_out/summary.txt
+done
+timeout 600 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "smoke exit $?" >> gpurun_out/summary.txt
+timeout 900 python bench.py --steps 5 --warmup 3 > gpurun_out/bench.log 2>&1; echo "bench exit $?" >> gpurun_out/summary.txt
+cat gpurun_out/summary.txt
+tail -5 gpurun_out/test_gpu_*.log
+tail -3 gpurun_out/smoke.log gpurun_out/bench.log

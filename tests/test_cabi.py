@@ -58,3 +58,32 @@ def test_cpu_tensor_is_rejected_loudly():
     m = TwoTowerModel(cfg)
     with pytest.raises(TTRError):
         m.encode_query(torch.tensor([[1, 2, 3]]))
+
+
+def test_binding_arity_and_types_match_header():
+    """Every ctypes signature has the same number of arguments, and pointer/integer/float kinds
+    in the same positions, as the prototype in include/ttr_b200.h."""
+    import ctypes
+    from twotowermlretrieval_b200 import _lib
+    text = (ROOT / "include" / "ttr_b200.h").read_text()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    protos = dict(re.findall(r"\b(ttr_[a-z0-9_]+)\s*\(([^)]*)\)\s*;", text))
+    kinds = {ctypes.c_void_p: "p", ctypes.c_int: "i", ctypes.c_int64: "l", ctypes.c_float: "f", ctypes.c_double: "d"}
+    for name, sig in _lib._SIGNATURES.items():
+        params = [p.strip() for p in protos[name].split(",") if p.strip() and p.strip() != "void"]
+        want = []
+        for p in params:
+            if "*" in p:
+                want.append("p")
+            elif p.startswith("int64_t"):
+                want.append("l")
+            elif p.startswith("int"):
+                want.append("i")
+            elif p.startswith("float"):
+                want.append("f")
+            elif p.startswith("double"):
+                want.append("d")
+            else:
+                raise AssertionError(f"{name}: cannot classify parameter {p!r}")
+        got = [kinds[a] for a in sig]
+        assert got == want, f"{name}: binding {got} vs header {want}"

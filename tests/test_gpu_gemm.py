@@ -1,0 +1,66 @@
+"""GPU parity: tcgen05 tf32 input-projection GEMM vs fp64, and vs the fp32 CUDA-core kernel."""
+import numpy as np
+import pytest
+import torch
+
+from twotowermlretrieval_b200 import _lib
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(name, A, W, bias, m_valid=None):
+    M, K = A.shape
+    N = W.shape[0]
+    C = torch.full((M, N), float("nan"), device=A.device)
+    mv = None if m_valid is None else torch.tensor([m_valid], dtype=torch.int32, device=A.device)
+    _lib.call(name, A, W, bias, C, M, mv, N, K)
+    torch.cuda.synchronize()
+    return C
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 32), (128, 128, 64), (1, 8, 4), (300, 1536, 200), (1000, 1536, 512),
+                                   (777, 96, 12), (129, 100, 36), (4096, 1536, 200)])
+def test_tf32_gemm_matches_fp64(cuda_device, M, N, K):
+    g = torch.Generator(device=cuda_device).manual_seed(M + N + K)
+    A = torch.randn(M, K, device=cuda_device, generator=g) * 0.4
+    W = (torch.rand(N, K, device=cuda_device, generator=g) - 0.5) / 8
+    b = torch.randn(N, device=cuda_device, generator=g) * 0.05
+    ref = (A.double() @ W.double().t() + b.double())
+    C = _run("ttr_gemm_tf32_bias", A, W, b)
+    scale = float((A.double().abs() @ W.double().abs().t()).max())
+    err = float((C.double() - ref).abs().max())
+    assert err <= 1.5e-3 * scale, (err, scale)          # tf32: 10-bit mantissa operands, fp32 accumulate
+    Cf = _run("ttr_debug_gemm_fp32_bias", A, W, b)
+    assert float((Cf.double() - ref).abs().max()) <= 1e-5 * max(scale, 1.0)
+
+
+def test_dynamic_row_count_leaves_tail_untouched(cuda_device):
+    A = torch.randn(1000, 200, device=cuda_device)
+    W = torch.randn(1536, 200, device=cuda_device) / 16
+    b = torch.zeros(1536, device=cuda_device)
+    C = _run("ttr_gemm_tf32_bias", A, W, b, m_valid=333)
+    assert torch.isnan(C[333:]).all() and not torch.isnan(C[:333]).any()
+    ref = A[:333].double() @ W.double().t()
+    assert float((C[:333].double() - ref).abs().max()) < 2e-2
+
+
+def test_tf32_operand_rounding_probe(cuda_device):
+    """Records how kind::tf32 treats fp32 operands (printed, only sanity-pinned): C[i, :] =
+    hw(1 + i * 2^-14) * hw(1) for a single non-zero k, under both tensor-map data types."""
+    A = torch.zeros(128, 32, device=cuda_device)
+    A[:, 0] = 1.0 + torch.arange(128, device=cuda_device, dtype=torch.float32) * 2.0 ** -14
+    W = torch.zeros(128, 32, device=cuda_device)
+    W[:, 0] = 1.0
+    b = torch.zeros(128, device=cuda_device)
+    res = {}
+    for flags, name in ((0, "TFLOAT32 map"), (2, "FLOAT32 map")):
+        _lib.call_nostream("ttr_debug_set_flags", flags)
+        try:
+            C = _run("ttr_gemm_tf32_bias", A, W, b)
+        finally:
+            _lib.call_nostream("ttr_debug_set_flags", 0)
+        steps = ((C[:, 0].double() - 1.0) * 2.0 ** 14).round().long().cpu().tolist()
+        res[name] = steps
+        print(f"\n[tf32 probe] {name}: hw(1 + i*2^-14) in units of 2^-14, i=0..47: {steps[:48]}")
+        assert all(abs(v - i) <= 16 for i, v in enumerate(steps))          # within one tf32 ulp (2^-10)
+    print("[tf32 probe] identical across map types:", res["TFLOAT32 map"] == res["FLOAT32 map"])

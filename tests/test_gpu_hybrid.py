@@ -1,0 +1,111 @@
+"""GPU parity: hybrid rerank kernel (frontend/main.py:158-198), QueryInferencer and
+SimpleHybridRetriever against the fixture produced by running the reference classes."""
+import json
+import pickle
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden_weights, load_golden
+from oracle import towers_numpy as onp
+from twotowermlretrieval_b200 import synth
+from twotowermlretrieval_b200.index import CsrF64, ShardedIndex, hybrid_rerank, search_topk, tfidf_candidates
+
+pytestmark = pytest.mark.gpu
+
+
+def _queries_csr(rng, B, F, device):
+    idx, val, ptr = [], [], [0]
+    for b in range(B):
+        k = 0 if b == 1 else int(rng.integers(2, 7))        # query 1 has no TF-IDF vocabulary hit
+        c = np.sort(rng.choice(F, size=k, replace=False))
+        v = rng.random(k) + 0.1
+        v = v / np.linalg.norm(v) if k else v
+        idx.append(c); val.append(v); ptr.append(ptr[-1] + k)
+    return (CsrF64.from_arrays(np.array(ptr), np.concatenate(idx) if idx else [], np.concatenate(val), device),
+            idx, val)
+
+
+@pytest.mark.parametrize("space", ["l2", "cosine"])
+@pytest.mark.parametrize("alpha", [1.0, 0.7, 0.3, 0.05])
+def test_rerank_matches_frontend_restatement(cuda_device, alpha, space):
+    rng = np.random.default_rng(17)
+    N, F, B, kc = 3000, 400, 6, 50
+    indptr, indices, data = synth.make_tfidf_csr(N, n_features=F, mean_nnz=12, seed=9)
+    docs = CsrF64.from_arrays(indptr, indices, data, cuda_device)
+    qcsr, qidx, qval = _queries_csr(rng, B, F, cuda_device)
+    D = synth.make_unit_rows(N, 256, seed=3)
+    Q = synth.make_unit_rows(B, 256, seed=4)
+    s, i = search_topk(torch.tensor(Q, device=cuda_device), torch.tensor(D, device=cuda_device), kc)
+    out = hybrid_rerank(i, s, alpha, docs_csr=docs, q_csr=qcsr, space=space, top_n=10)
+    sc, ic = s.cpu().numpy(), i.cpu().numpy()
+    for b in range(B):
+        order, fin, sem, tf = onp.hybrid_rerank_frontend(ic[b], sc[b], indptr, indices, data, qidx[b], qval[b],
+                                                        alpha, top_n=10, space=space)
+        np.testing.assert_array_equal(out["pos"][b].cpu().numpy(), order)
+        np.testing.assert_allclose(out["final"][b].cpu().numpy(), fin, rtol=0, atol=1e-15)
+        np.testing.assert_allclose(out["tfidf"][b].cpu().numpy(), tf, rtol=0, atol=1e-15)
+        np.testing.assert_array_equal(out["idx"][b].cpu().numpy(), ic[b][order])
+    if alpha == 1.0:
+        assert (out["pos"].cpu().numpy() == np.arange(10)).all()      # stable sort keeps dense order
+
+
+def test_sharded_hybrid_single_rank_and_candidate_tfidf(cuda_device):
+    rng = np.random.default_rng(3)
+    N, F, B = 2000, 300, 4
+    indptr, indices, data = synth.make_tfidf_csr(N, n_features=F, mean_nnz=10, seed=2)
+    docs = CsrF64.from_arrays(indptr, indices, data, cuda_device)
+    qcsr, qidx, qval = _queries_csr(rng, B, F, cuda_device)
+    D = torch.tensor(synth.make_unit_rows(N, 256, seed=5), device=cuda_device)
+    Q = torch.tensor(synth.make_unit_rows(B, 256, seed=6), device=cuda_device)
+    idx = ShardedIndex(D, 0, N, tfidf_local=docs)
+    out = idx.search_hybrid(Q, qcsr, alpha=0.4, k=50, top_n=10)
+    s, i = search_topk(Q, D, 50)
+    direct = hybrid_rerank(i, s, 0.4, docs_csr=docs, q_csr=qcsr, top_n=10)
+    assert torch.equal(out["idx"], direct["idx"]) and torch.equal(out["final"], direct["final"])
+    # a shard only scores the rows it owns
+    half = docs.row_slice(1000, 2000)
+    tf_half = tfidf_candidates(i, half, qcsr)
+    tf_full = tfidf_candidates(i, docs, qcsr)
+    own = (i >= 1000)
+    assert torch.equal(tf_half[own], tf_full[own]) and (tf_half[~own] == 0).all()
+
+
+def test_inferencer_and_simple_hybrid_match_reference_run(cuda_device, tmp_path):
+    g = load_golden("inferencer_hybrid")
+    cfg = g["cfg"]
+    words = json.loads(str(g["words"]))
+    docs = json.loads(str(g["docs"]))
+    queries = json.loads(str(g["queries"]))
+    art = tmp_path / "run"
+    art.mkdir()
+    with open(art / "word_to_idx.pkl", "wb") as f:
+        pickle.dump({w: i for i, w in enumerate(words)}, f)
+    torch.save({k: torch.tensor(v) for k, v in golden_weights(g).items()}, art / "model.pth")
+    small = {k: v for k, v in cfg.items() if k != "VOCAB_SIZE"}
+    (art / "config.json").write_text(json.dumps(small))
+    from twotowermlretrieval_b200.query_inferencer import QueryInferencer
+    from twotowermlretrieval_b200.simple_hybrid import SimpleHybridRetriever
+    inf = QueryInferencer(str(art), device=cuda_device)
+    assert inf.config["VOCAB_SIZE"] == len(words) + 1
+    z = inf.get_query_embedding("")
+    assert z.shape == (cfg["HIDDEN_DIM"],) and z.dtype == np.float32 and not z.any()     # query_inferencer.py:65-69
+    r = SimpleHybridRetriever(str(art), alpha=float(g["alpha"]), device=cuda_device)
+    r.fit(docs)
+    np.testing.assert_allclose(r.doc_embeddings, g["doc_emb"], rtol=0, atol=3e-4)
+    for qi, q in enumerate(queries):
+        if g["raises"][qi]:
+            with pytest.raises(RuntimeError):
+                inf.get_query_embedding(q)
+            continue
+        e = inf.get_query_embedding(q)
+        np.testing.assert_allclose(e, g["query_emb"][qi], rtol=0, atol=3e-4)
+        res = r.search(q, top_k=10)
+        got_idx = [docs.index(d) for d, _ in res]
+        got_sc = np.array([s for _, s in res])
+        np.testing.assert_allclose(got_sc, g["res_score"][qi], rtol=0, atol=5e-4)
+        want = g["res_idx"][qi].tolist()
+        assert got_idx == want or np.abs(np.diff(g["res_score"][qi])).min() < 1e-3
+    batch = inf.encode_queries([q for qi, q in enumerate(queries) if not g["raises"][qi]] + [""])
+    assert batch.shape[0] == 5 and not batch[-1].any()

@@ -1,0 +1,112 @@
+"""GPU parity: fused cosine top-k / merge kernels vs the oracle (evaluators.py:185-186)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+from gpu_util import check_topk
+from oracle import towers_numpy as onp
+from twotowermlretrieval_b200 import synth
+from twotowermlretrieval_b200.index import search_topk, topk_merge
+
+pytestmark = pytest.mark.gpu
+
+
+def test_golden_fixture(cuda_device):
+    g = load_golden("search")
+    D = synth.make_unit_rows(int(g["n_docs"]), 256, seed=int(g["doc_seed"]))
+    Q = synth.make_unit_rows(5, 256, seed=int(g["query_seed"]))
+    s, i = search_topk(torch.tensor(Q, device=cuda_device), torch.tensor(D, device=cuda_device), 50)
+    np.testing.assert_allclose(s.cpu().numpy(), g["scores"], rtol=1e-3, atol=2e-5)
+    assert (i.cpu().numpy() == g["idx"]).mean() > 0.99
+    check_topk(s, i, Q, D, 50)
+
+
+@pytest.mark.parametrize("B", [1, 2, 3, 4, 7, 8, 9, 21])
+@pytest.mark.parametrize("N", [1, 31, 32, 33, 257, 5000])
+def test_small_and_ragged_shapes(cuda_device, B, N):
+    D = synth.make_unit_rows(N, 256, seed=100 + N)
+    Q = synth.make_unit_rows(B, 256, seed=200 + B)
+    k = 50
+    s, i = search_topk(torch.tensor(Q, device=cuda_device), torch.tensor(D, device=cuda_device), k, row_offset=1000)
+    kk = min(k, N)
+    check_topk(s[:, :kk], i[:, :kk], Q, D, kk, row_offset=1000)
+    if N < k:                                # unfilled slots are flagged, not garbage
+        assert (i[:, N:] == -1).all() and torch.isinf(s[:, N:]).all()
+
+
+@pytest.mark.parametrize("k", [1, 5, 10, 50, 64])
+def test_k_values(cuda_device, k):
+    D = synth.make_unit_rows(3000, 256, seed=7)
+    Q = synth.make_unit_rows(6, 256, seed=8)
+    s, i = search_topk(torch.tensor(Q, device=cuda_device), torch.tensor(D, device=cuda_device), k)
+    assert check_topk(s, i, Q, D, k) == 0
+    assert (np.diff(s.cpu().numpy(), axis=1) <= 0).all()
+
+
+def test_adversarial_orders_and_ties(cuda_device):
+    rng = np.random.default_rng(0)
+    q = synth.make_unit_rows(1, 256, seed=1)
+    # ascending scores: every document beats the running threshold -> constant compaction
+    N = 6000
+    D = rng.standard_normal((N, 256)).astype(np.float32) * 0.01
+    D += np.linspace(-1, 1, N, dtype=np.float32)[:, None] * q
+    s, i = search_topk(torch.tensor(q, device=cuda_device), torch.tensor(D, device=cuda_device), 50)
+    check_topk(s, i, q, D, 50)
+    # all-equal documents: exact ties resolve to the lowest indices, in order
+    D2 = np.repeat(synth.make_unit_rows(1, 256, seed=2), 4000, axis=0)
+    s, i = search_topk(torch.tensor(q, device=cuda_device), torch.tensor(D2, device=cuda_device), 50)
+    assert i.cpu().tolist()[0] == list(range(50))
+    # duplicated blocks: each winner appears with all its copies, lowest index first
+    base = synth.make_unit_rows(500, 256, seed=3)
+    D3 = np.concatenate([base, base, base])
+    s, i = search_topk(torch.tensor(q, device=cuda_device), torch.tensor(D3, device=cuda_device), 30)
+    ii = i.cpu().numpy()[0]
+    assert (ii[0::3] + 500 == ii[1::3]).all() and (ii[1::3] + 500 == ii[2::3]).all()
+
+
+def test_merge_kernel_matches_oracle(cuda_device):
+    rng = np.random.default_rng(5)
+    P, B, kin, k = 7, 9, 50, 50
+    s = np.sort(rng.standard_normal((P, B, kin)).astype(np.float32), axis=2)[:, :, ::-1].copy()
+    i = rng.permutation(P * B * kin).reshape(P, B, kin).astype(np.int64)
+    s[2, :, 10:] = s[3, :, 10:]                                  # cross-list ties
+    ms, mi = topk_merge(torch.tensor(s, device=cuda_device), torch.tensor(i, device=cuda_device), k)
+    cs = s.transpose(1, 0, 2).reshape(B, -1)
+    ci = i.transpose(1, 0, 2).reshape(B, -1)
+    order = np.lexsort((ci, -cs), axis=1)[:, :k]
+    np.testing.assert_array_equal(mi.cpu().numpy(), np.take_along_axis(ci, order, 1))
+    np.testing.assert_array_equal(ms.cpu().numpy(), np.take_along_axis(cs, order, 1))
+
+
+def test_sharded_equals_unsharded(cuda_device):
+    """Row shards + merge == one matrix (the multi-GPU scheme, emulated on one device)."""
+    D = synth.make_unit_rows(10007, 256, seed=11)
+    Q = synth.make_unit_rows(5, 256, seed=12)
+    Dd, Qd = torch.tensor(D, device=cuda_device), torch.tensor(Q, device=cuda_device)
+    s_full, i_full = search_topk(Qd, Dd, 50)
+    from twotowermlretrieval_b200.index import shard_bounds
+    parts = []
+    for r in range(3):
+        lo, hi = shard_bounds(D.shape[0], 3, r)
+        parts.append(search_topk(Qd, Dd[lo:hi].contiguous(), 50, row_offset=lo))
+    ms, mi = topk_merge(torch.stack([p[0] for p in parts]), torch.stack([p[1] for p in parts]), 50)
+    assert torch.equal(mi, i_full) and torch.equal(ms, s_full)
+
+
+def test_million_docs_properties(cuda_device):
+    """BASELINE configs[1] size: N=1M, B=1 and 8 — checked against torch on the same device in
+    chunks (size-independent properties: sorted, unique, every reported score is the true dot,
+    nothing outside the list beats the k-th)."""
+    gen = torch.Generator(device=cuda_device).manual_seed(3)
+    D = torch.nn.functional.normalize(torch.randn(1_000_000, 256, device=cuda_device, generator=gen), dim=1)
+    Q = torch.nn.functional.normalize(torch.randn(8, 256, device=cuda_device, generator=gen), dim=1)
+    for B in (1, 8):
+        s, i = search_topk(Q[:B], D, 50)
+        full = (Q[:B].double() @ D.double().t())
+        ref_s, ref_i = torch.topk(full, 50, dim=1)
+        assert torch.allclose(s.double(), ref_s, rtol=1e-3, atol=2e-5)
+        assert (torch.diff(s, dim=1) <= 0).all()
+        got = torch.gather(full, 1, i)
+        assert torch.allclose(got, ref_s, rtol=1e-3, atol=2e-5)
+        assert (i == ref_i).float().mean() > 0.98

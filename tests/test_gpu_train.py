@@ -1,0 +1,173 @@
+"""GPU parity: triplet loss, backward pass, clip+Adam step vs fixtures from the reference's
+live loop (main.py:244-259) and vs torch autograd on the oracle."""
+import json
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden_weights, load_golden
+from gpu_util import model_from_numpy
+from oracle import torch_path
+from twotowermlretrieval_b200 import _lib, synth, triplet_loss_cosine
+from twotowermlretrieval_b200.optim import FusedClipAdam
+from twotowermlretrieval_b200.trainer import TrainerFactory
+
+pytestmark = pytest.mark.gpu
+
+
+def test_triplet_loss_forward_backward_vs_torch(cuda_device):
+    g = torch.Generator().manual_seed(0)
+    for B, H, margin in [(7, 16, 0.5), (64, 256, 0.5), (300, 256, 0.2), (5, 8, 1.0)]:
+        q, p, n = (torch.randn(B, H, generator=g) for _ in range(3))
+        q = torch.nn.functional.normalize(q, dim=1)
+        qd, pd_, nd = (t.clone().to(cuda_device).requires_grad_(True) for t in (q, p, n))
+        loss = triplet_loss_cosine((qd, pd_, nd), margin=margin)
+        (loss * 1.7).backward()
+        qc, pc, nc = (t.clone().requires_grad_(True) for t in (q, p, n))
+        ref = torch_path.triplet_loss_cosine(qc, pc, nc, margin)
+        (ref * 1.7).backward()
+        assert abs(float(loss) - float(ref)) < 1e-6
+        for a, b in ((qd, qc), (pd_, pc), (nd, nc)):
+            assert torch.allclose(a.grad.cpu(), b.grad, atol=1e-6, rtol=1e-4)
+
+
+def test_batch_metrics_vs_oracle(cuda_device):
+    from oracle import towers_numpy as onp
+    g = load_golden("cfgdims")
+    t = TrainerFactory.create_trainer({"LR": 1e-3}, model_from_numpy(g["cfg"], synth.make_state_dict(g["cfg"]), cuda_device),
+                                      cuda_device)
+    q, p, n = (torch.tensor(g[k], device=cuda_device) for k in ("q_emb", "p_emb", "n_emb"))
+    got = t.compute_batch_metrics(q, p, n)
+    want = onp.batch_metrics(g["q_emb"], g["p_emb"], g["n_emb"])
+    for k in want:
+        assert abs(got[k] - want[k]) < 1e-5, k
+    rec = t.compute_recall_metrics(q, torch.cat([p, n]), k_values=[5, 10])
+    sim = torch.tensor(g["q_emb"]) @ torch.cat([torch.tensor(g["p_emb"]), torch.tensor(g["n_emb"])]).t()
+    top = sim.topk(10, dim=1).indices
+    for k in (5, 10):
+        want_r = float(np.mean([i in top[i, :k] for i in range(q.shape[0])]))
+        assert abs(rec[f"recall_at_{k}"] - want_r) < 1e-6
+
+
+@pytest.mark.parametrize("name", ["small_bi2", "small_uni1", "small_uni2", "small_bi1_trainable_table"])
+def test_gradients_match_reference_fixture(cuda_device, name):
+    g = load_golden(name)
+    cfg = g["cfg"]
+    m = model_from_numpy(cfg, golden_weights(g), cuda_device, pretrained=bool(g["pretrained"])).train()
+    q, p, n = (torch.tensor(g[k], device=cuda_device) for k in ("q", "p", "n"))
+    loss = triplet_loss_cosine((m.encode_query(q), m.encode_document(p), m.encode_document(n)), margin=cfg["MARGIN"])
+    loss.backward()
+    assert abs(float(loss) - float(g["train_loss"])) < 2e-4
+    worst = 0.0
+    for k, param in m.named_parameters():
+        if f"g::{k}" not in g:
+            continue
+        want = g[f"g::{k}"]
+        got = param.grad.detach().cpu().numpy() if param.grad is not None else np.zeros_like(want)
+        scale = max(np.abs(want).max(), 1e-6)
+        err = np.abs(got - want).max() / scale
+        worst = max(worst, err)
+        assert err < 2e-2, (k, err)
+    total = float(torch.nn.utils.clip_grad_norm_(m.parameters(), 1e9))
+    assert abs(total - float(g["grad_norm"])) < 5e-3 * float(g["grad_norm"])
+    print(f"\n[{name}] worst relative grad error {worst:.2e}")
+
+
+@pytest.mark.parametrize("name", ["small_bi2", "small_uni2"])
+def test_reference_loop_with_torch_adam_is_drop_in(cuda_device, name):
+    """main.py:244-259 verbatim: torch.optim.Adam + clip_grad_norm_ on our module."""
+    g = load_golden(name)
+    cfg = g["cfg"]
+    m = model_from_numpy(cfg, golden_weights(g), cuda_device).train()
+    opt = torch.optim.Adam(m.parameters(), lr=cfg["LR"])
+    q, p, n = (torch.tensor(g[k], device=cuda_device) for k in ("q", "p", "n"))
+    opt.zero_grad()
+    loss = triplet_loss_cosine((m.encode_query(q), m.encode_document(p), m.encode_document(n)), margin=cfg["MARGIN"])
+    loss.backward()
+    torch.nn.utils.clip_grad_norm_(m.parameters(), max_norm=1.0)
+    opt.step()
+    lr = cfg["LR"]
+    for k, v in m.state_dict().items():
+        if f"a::{k}" in g:
+            got, want = v.cpu().numpy(), g[f"a::{k}"]
+            # Adam's first step moves every element by ~lr*sign(g): elements whose gradient is ~eps can
+            # land anywhere in [-lr, lr], so a handful may differ by up to 2*lr; everything else is tight.
+            close = np.isclose(got, want, rtol=2e-3, atol=2e-5)
+            assert close.mean() > 0.995, (k, close.mean())
+            assert np.abs(got - want).max() <= 2.05 * lr, k
+
+
+def test_cfgdims_two_fused_steps_match_reference(cuda_device):
+    g = load_golden("cfgdims")
+    cfg = g["cfg"]
+    m = model_from_numpy(cfg, synth.make_state_dict(cfg, seed=0, table_seed=1), cuda_device).train()
+    opt = FusedClipAdam(m, lr=cfg["LR"], max_norm=1.0)
+    q, p, n = (torch.tensor(g[k], device=cuda_device) for k in ("q", "p", "n"))
+    grad_l2 = json.loads(str(g["grad_l2"]))
+    for step in range(2):
+        opt.zero_grad()
+        loss = triplet_loss_cosine((m.encode_query(q), m.encode_document(p), m.encode_document(n)), margin=0.5)
+        loss.backward()
+        if step == 0:
+            for k, param in m.named_parameters():
+                if k in grad_l2:
+                    got = float(param.grad.norm())
+                    assert abs(got - grad_l2[k]) <= 2e-2 * grad_l2[k] + 1e-6, (k, got, grad_l2[k])
+                    head = param.grad.detach().reshape(-1)[:64].cpu().numpy()
+                    want = g[f"gh::{k}"]
+                    assert np.abs(head - want).max() <= 2e-2 * max(np.abs(want).max(), 1e-5), k
+        opt.step()
+        assert abs(float(loss) - g["train_losses"][step]) < 3e-4
+        assert abs(float(opt.last_grad_norm) - g["grad_norms"][step]) < 1e-2 * g["grad_norms"][step]
+    for k, v in m.state_dict().items():
+        if f"ah::{k}" in g:
+            np.testing.assert_allclose(v.reshape(-1)[:64].cpu().numpy(), g[f"ah::{k}"], rtol=1e-3, atol=2e-5, err_msg=k)
+
+
+def test_clip_adam_kernel_vs_torch(cuda_device):
+    torch.manual_seed(0)
+    n = 100003
+    p0 = torch.randn(n)
+    g0 = torch.randn(n) * 0.01
+    for max_norm in (1.0, None):
+        t = p0.clone().requires_grad_(True)
+        opt = torch.optim.Adam([t], lr=5e-5)
+        p = p0.clone().to(cuda_device)
+        m = torch.zeros_like(p)
+        v = torch.zeros_like(p)
+        ws = torch.empty(1024, device=cuda_device)
+        norm = torch.zeros(1, device=cuda_device)
+        for step in (1, 2, 3):
+            gg = g0 * step
+            t.grad = gg.clone()
+            tot = torch.nn.utils.clip_grad_norm_([t], max_norm) if max_norm else t.grad.norm()
+            opt.step()
+            _lib.call("ttr_clip_adam", p, gg.to(cuda_device), m, v, n, 1.0, float(max_norm or -1.0), 5e-5, 0.9, 0.999,
+                      1e-8, step, norm, ws)
+            assert abs(float(norm) - float(tot)) < 1e-4 * float(tot)
+            assert torch.allclose(p.cpu(), t.detach(), rtol=1e-5, atol=1e-7)
+
+
+def test_dropout_train_mode_replays_through_oracle(cuda_device):
+    """Train-mode forward with dropout 0.2: export our packed masks, replay them in the oracle."""
+    g = load_golden("small_bi2")
+    cfg = dict(g["cfg"], DROPOUT=0.2)
+    m = model_from_numpy(cfg, golden_weights(g), cuda_device).train()
+    x = torch.tensor(g["p"], device=cuda_device)
+    with torch.no_grad():
+        out = m.encode_document(x)
+    enc = m.doc_encoder
+    plan, mask = enc.last_plan, enc.last_dropout_masks[0]
+    assert mask is not None and 0.05 < float((mask == 0).float().mean()) < 0.4
+    B, T = x.shape
+    order, offs = plan.order.cpu().numpy(), plan.offsets.cpu().numpy()
+    padded = torch.ones(B, T, mask.shape[1])
+    mc = mask.cpu()
+    for s in range(B):
+        ln = offs[s + 1] - offs[s]
+        padded[order[s], :ln] = mc[offs[s]:offs[s + 1]]
+    sd = torch_path.to_torch_state(golden_weights(g))
+    with torch.no_grad():
+        ref = torch_path.encoder_forward(sd, "doc_encoder", x.cpu(), cfg, dropout_masks=[padded])
+    assert torch.allclose(out.cpu(), ref, atol=2e-4)

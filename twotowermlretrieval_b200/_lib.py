@@ -29,7 +29,7 @@ _SIGNATURES = {
     "ttr_gemm_nn_fp32": [P, P, P, I32, P, I32, I32, I32, P],
     "ttr_gru_recurrence_fwd": [P, P, P, P, P, I32, I32, I32, P, P, P, P],
     "ttr_gru_recurrence_bwd": [P, P, P, P, P, P, P, I32, I32, I32, P, P, P],
-    "ttr_gru_whh_grad": [P, P, P, P, P, I32, I32, I32, P, P, P, I32, P],
+    "ttr_gru_whh_grad": [P, P, P, I32, I32, I32, I32, P, P, I32, P],
     "ttr_proj_l2norm_fwd": [P, P, P, I32, I32, I32, I32, P, P, P],
     "ttr_l2norm_bwd": [P, P, I32, I32, I32, P, P],
     "ttr_triplet_fwd": [P, P, P, I32, I32, F32, P, P],
