@@ -256,7 +256,9 @@ def run_b200(args):
 
     hbm_peak, peak_src, _ = peaks()
     shard_rows = hi - lo
-    passes = -(-B // 8)                                  # the streaming kernel handles 8 queries per pass
+    # B <= 8: CUDA-core streaming kernel, one pass; B > 8: tcgen05 kernel, one HBM pass per call
+    # (query tiles of 128 share document tiles through L2)
+    passes = 1
     algo_bytes = shard_rows * BYTES_PER_DOC * passes     # per search call on this rank
     achieved = algo_bytes / (ms_kern * 1e-3) / 1e9
     line = {
@@ -266,10 +268,11 @@ def run_b200(args):
         "config": bench_config(args, world),
         "e2e": {"value": B / (ms_e2e * 1e-3), "unit": "queries/s", "h2d_bytes_per_step": B * DIM * 4,
                 "d2h_bytes_per_step": B * TOPK * 12, "ms_per_step": ms_e2e},
-        "gpu_launches": K * (passes + 1 + (1 if world > 1 else 0)),
+        "gpu_launches": K * ((1 if B <= 8 else 2) + 1 + (1 if world > 1 else 0)),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                      "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
-                     "kernel": "score_topk_stream_kernel (+ topk_merge_kernel, <1% of the call)",
+                     "kernel": ("score_topk_stream_kernel" if B <= 8 else "score_topk_mma_kernel") +
+                               " (+ topk_merge_kernel, ~1% of the call)",
                      "algorithmic_bytes_per_call": algo_bytes, "ms_per_call": ms_kern,
                      "passes_over_shard_per_call": passes},
         "clocks": clocks,

@@ -112,8 +112,12 @@ int ttr_embed_scatter_grad(const int64_t* ids, int B, int T, int64_t V, int E,
 int ttr_colsum(const float* A, int m_bound, const int32_t* m_valid, int N, float* out,
                int accumulate, void* stream);
 /* Test/debug switches: bit0 = force the generic (any-H) GRU kernels, bit1 = encode TMA maps
- * as FLOAT32 instead of TFLOAT32. */
+ * as FLOAT32 instead of TFLOAT32 (hardware truncation instead of round-to-nearest),
+ * bit2 = force the CUDA-core streaming scorer for every batch size. */
 int ttr_debug_set_flags(int flags);
+/* Diagnostic: device buffer (5 * 256 int64) receiving the pipeline timeline (SM clock at five
+ * events per document tile) of CTA (0,0) of the tcgen05 scorer; NULL switches it off. */
+int ttr_debug_set_trace(long long* trace);
 
 /* ---- K5/K6: projection + L2 normalise --------------------------------------------------
  * Replaces `cat(h_n[-2], h_n[-1])` -> `self.projection` -> `F.normalize(p=2, dim=1)`
@@ -157,6 +161,8 @@ int ttr_clip_adam(float* params, const float* grads, float* exp_avg, float* exp_
  * materialises [B, N].
  * Q fp32 [B, D]; docs fp32 [N, D] row-major (the document_embeddings.npy layout,
  * backend/main.py:138); D must be 256 for the fused kernels; k <= 64.
+ * B <= 8: CUDA-core streaming kernel (fp32 exact products, HBM-bound);
+ * B  > 8: tcgen05 kind::tf32 kernel, 128 queries per pass (scores within 1e-3 relative).
  * row_offset is added to the emitted indices (global ids of a row shard).
  * out_scores fp32 [B, k] descending; out_idx int64 [B, k]; ties: lower index first.
  * workspace: ttr_score_topk_workspace_bytes(B, N, k) bytes. */

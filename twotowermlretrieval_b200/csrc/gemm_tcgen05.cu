@@ -61,51 +61,55 @@ gemm_tf32_bias_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ===== TMA producer =====
-    if (lane == 0) {
+    // ===== TMA producer (whole warp runs the loop; one elected lane issues) =====
+    if (ptx::elect_one()) {
       ptx::prefetch_tensormap(&map_a);
       ptx::prefetch_tensormap(&map_w);
-      int it = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int m0 = (tile / n_tiles) * GM, n0 = (tile % n_tiles) * GN;
-        for (int kb = 0; kb < k_blocks; ++kb, ++it) {
-          const int s = it % G_STAGES;
-          const uint32_t ph = (uint32_t)(it / G_STAGES) & 1u;
-          ptx::mbar_wait(empty_bar + s, ph ^ 1u);
+    }
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int m0 = (tile / n_tiles) * GM, n0 = (tile % n_tiles) * GN;
+      for (int kb = 0; kb < k_blocks; ++kb, ++it) {
+        const int s = it % G_STAGES;
+        const uint32_t ph = (uint32_t)(it / G_STAGES) & 1u;
+        ptx::mbar_wait(empty_bar + s, ph ^ 1u);
+        unsigned char* a_dst = tiles + s * G_STAGE_BYTES;
+        if (ptx::elect_one()) {
           ptx::mbar_arrive_expect_tx(full_bar + s, G_STAGE_BYTES);
-          unsigned char* a_dst = tiles + s * G_STAGE_BYTES;
           ptx::tma_load_2d(a_dst, &map_a, kb * GK, m0, full_bar + s);
           ptx::tma_load_2d(a_dst + G_A_BYTES, &map_w, kb * GK, n0, full_bar + s);
         }
+        __syncwarp();
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer (one thread) =====
-    if (lane == 0) {
-      constexpr uint32_t idesc = ptx::make_idesc_tf32(GM, GN);
-      int it = 0, local = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
-        const int buf = local & 1;
-        const uint32_t aph = (uint32_t)(local >> 1) & 1u;
-        ptx::mbar_wait(acc_empty + buf, aph ^ 1u);       // epilogue drained this accumulator
+    // ===== MMA issuer (whole warp runs the loop; one elected lane issues) =====
+    constexpr uint32_t idesc = ptx::make_idesc_tf32(GM, GN);
+    int it = 0, local = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
+      const int buf = local & 1;
+      const uint32_t aph = (uint32_t)(local >> 1) & 1u;
+      ptx::mbar_wait(acc_empty + buf, aph ^ 1u);       // epilogue drained this accumulator
+      ptx::tc_fence_after_sync();
+      const uint32_t d_tmem = tmem_base + buf * G_ACC_COLS;
+      for (int kb = 0; kb < k_blocks; ++kb, ++it) {
+        const int s = it % G_STAGES;
+        const uint32_t ph = (uint32_t)(it / G_STAGES) & 1u;
+        ptx::mbar_wait(full_bar + s, ph);
         ptx::tc_fence_after_sync();
-        const uint32_t d_tmem = tmem_base + buf * G_ACC_COLS;
-        for (int kb = 0; kb < k_blocks; ++kb, ++it) {
-          const int s = it % G_STAGES;
-          const uint32_t ph = (uint32_t)(it / G_STAGES) & 1u;
-          ptx::mbar_wait(full_bar + s, ph);
-          ptx::tc_fence_after_sync();
-          const uint32_t a_addr = ptx::smem_u32(tiles + s * G_STAGE_BYTES);
-          const uint64_t a_desc = ptx::make_kmajor_sw128_desc(a_addr);
-          const uint64_t b_desc = ptx::make_kmajor_sw128_desc(a_addr + G_A_BYTES);
+        const uint32_t a_addr = ptx::smem_u32(tiles + s * G_STAGE_BYTES);
+        const uint64_t a_desc = ptx::make_kmajor_sw128_desc(a_addr);
+        const uint64_t b_desc = ptx::make_kmajor_sw128_desc(a_addr + G_A_BYTES);
+        if (ptx::elect_one()) {
 #pragma unroll
           for (int k = 0; k < GK / 8; ++k) {
             // advance 8 tf32 = 32 bytes inside the 128-byte swizzle row: +2 in 16-byte units
             ptx::mma_tf32_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
           }
           ptx::mma_commit(empty_bar + s);                 // smem slot free once these MMAs retire
+          if (kb == k_blocks - 1) ptx::mma_commit(acc_full + buf);   // accumulator complete
         }
-        ptx::mma_commit(acc_full + buf);                  // accumulator complete
+        __syncwarp();
       }
     }
   } else if (warp >= 4) {

@@ -7,6 +7,8 @@
 // (values are scattered across lanes instead of all-reduced, 5 shuffle rounds in total),
 // and filters scores against a per-(warp,query) running k-th best held in shared memory.
 // The [B, N] score matrix is never written.  Algorithmic traffic: N * 1024 B per pass.
+// (Batches > 8 go to the tcgen05 kernel in score_topk_mma.cu; debug flag bit 2 forces this
+// kernel for any batch so the tests can compare the two paths.)
 #include "ptx.cuh"
 #include "topk_common.cuh"
 
@@ -15,6 +17,8 @@ namespace ttr {
 constexpr int DIM = 256;
 constexpr int SC_WARPS = 8;
 constexpr int SC_THREADS = SC_WARPS * 32;
+
+extern int g_debug_flags;
 
 // Halving butterfly: NV per-lane partial values -> each value fully summed in exactly
 // max(NV/32,1) slots: value index = lane * (NV/32) + i for NV >= 32, lane >> (5 - log2 NV)
@@ -311,10 +315,19 @@ static int launch_stream(const float* Q, int nq, const float* docs, int64_t N, i
   return TTR_OK;
 }
 
+int launch_score_topk_mma(const float* Q, int B, const float* docs, int64_t N, int k, void* workspace,
+                          float** part_s_out, int32_t** part_i_out, int* parts_out, cudaStream_t st);
+int64_t score_topk_mma_workspace_bytes(int B, int k);
+
+// Query batches up to this size run the CUDA-core streaming kernel (HBM-bound up to ~4
+// queries per pass); larger batches run the tcgen05 kernel (128 queries per pass).
+constexpr int STREAM_MAX_B = 8;
+
 }  // namespace ttr
 
 extern "C" int64_t ttr_score_topk_workspace_bytes(int B, int64_t N, int k) {
   (void)N;
+  if (B > ttr::STREAM_MAX_B && !(ttr::g_debug_flags & 4)) return ttr::score_topk_mma_workspace_bytes(B, k);
   int parts = ttr::simt_grid_parts();
   int64_t bp = (int64_t)((B + 7) / 8) * 8;
   return bp * parts * (int64_t)k * 8 + 256;
@@ -331,6 +344,15 @@ extern "C" int ttr_score_topk(const float* Q, int B, const float* docs, int64_t 
   TTR_REQUIRE(workspace_bytes >= ttr_score_topk_workspace_bytes(B, N, k), "ttr_score_topk: workspace too small");
   TTR_REQUIRE(((uintptr_t)docs & 15) == 0 && ((uintptr_t)Q & 15) == 0, "ttr_score_topk: Q/docs must be 16-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
+  if (B > STREAM_MAX_B && !(g_debug_flags & 4)) {
+    float* ps; int32_t* pi; int nparts;
+    int rc = launch_score_topk_mma(Q, B, docs, N, k, workspace, &ps, &pi, &nparts, st);
+    if (rc != TTR_OK) return rc;
+    topk_merge_kernel<int32_t><<<B, SC_THREADS, 0, st>>>(ps, pi, nparts, B, k, (int64_t)k, (int64_t)nparts * k, k,
+                                                       row_offset, out_scores, out_idx);
+    TTR_CHECK_LAUNCH();
+    return TTR_OK;
+  }
   const int parts = simt_grid_parts();
   const int64_t bp = (int64_t)((B + 7) / 8) * 8;
   float* part_s = reinterpret_cast<float*>(workspace);
