@@ -115,7 +115,7 @@ int ttr_colsum(const float* A, int m_bound, const int32_t* m_valid, int N, float
  * as FLOAT32 instead of TFLOAT32 (hardware truncation instead of round-to-nearest),
  * bit2 = force the CUDA-core streaming scorer for every batch size. */
 int ttr_debug_set_flags(int flags);
-/* Diagnostic: device buffer (5 * 256 int64) receiving the pipeline timeline (SM clock at five
+/* Diagnostic: device buffer (8 * 256 int64) receiving the pipeline timeline (SM clock at five
  * events per document tile) of CTA (0,0) of the tcgen05 scorer; NULL switches it off. */
 int ttr_debug_set_trace(long long* trace);
 

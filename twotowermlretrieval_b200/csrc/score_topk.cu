@@ -315,9 +315,9 @@ static int launch_stream(const float* Q, int nq, const float* docs, int64_t N, i
   return TTR_OK;
 }
 
-int launch_score_topk_mma(const float* Q, int B, const float* docs, int64_t N, int k, void* workspace,
-                          float** part_s_out, int32_t** part_i_out, int* parts_out, cudaStream_t st);
-int64_t score_topk_mma_workspace_bytes(int B, int k);
+int launch_score_topk_mma(const float* Q, int B, const float* docs, int64_t N, int k, int64_t row_offset,
+                          void* workspace, float* out_scores, int64_t* out_idx, cudaStream_t st);
+int64_t score_topk_mma_workspace_bytes(int B, int64_t N);
 
 // Query batches up to this size run the CUDA-core streaming kernel (HBM-bound up to ~4
 // queries per pass); larger batches run the tcgen05 kernel (128 queries per pass).
@@ -326,8 +326,7 @@ constexpr int STREAM_MAX_B = 8;
 }  // namespace ttr
 
 extern "C" int64_t ttr_score_topk_workspace_bytes(int B, int64_t N, int k) {
-  (void)N;
-  if (B > ttr::STREAM_MAX_B && !(ttr::g_debug_flags & 4)) return ttr::score_topk_mma_workspace_bytes(B, k);
+  if (B > ttr::STREAM_MAX_B && !(ttr::g_debug_flags & 4)) return ttr::score_topk_mma_workspace_bytes(B, N);
   int parts = ttr::simt_grid_parts();
   int64_t bp = (int64_t)((B + 7) / 8) * 8;
   return bp * parts * (int64_t)k * 8 + 256;
@@ -344,15 +343,8 @@ extern "C" int ttr_score_topk(const float* Q, int B, const float* docs, int64_t 
   TTR_REQUIRE(workspace_bytes >= ttr_score_topk_workspace_bytes(B, N, k), "ttr_score_topk: workspace too small");
   TTR_REQUIRE(((uintptr_t)docs & 15) == 0 && ((uintptr_t)Q & 15) == 0, "ttr_score_topk: Q/docs must be 16-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
-  if (B > STREAM_MAX_B && !(g_debug_flags & 4)) {
-    float* ps; int32_t* pi; int nparts;
-    int rc = launch_score_topk_mma(Q, B, docs, N, k, workspace, &ps, &pi, &nparts, st);
-    if (rc != TTR_OK) return rc;
-    topk_merge_kernel<int32_t><<<B, SC_THREADS, 0, st>>>(ps, pi, nparts, B, k, (int64_t)k, (int64_t)nparts * k, k,
-                                                       row_offset, out_scores, out_idx);
-    TTR_CHECK_LAUNCH();
-    return TTR_OK;
-  }
+  if (B > STREAM_MAX_B && !(g_debug_flags & 4))
+    return launch_score_topk_mma(Q, B, docs, N, k, row_offset, workspace, out_scores, out_idx, st);
   const int parts = simt_grid_parts();
   const int64_t bp = (int64_t)((B + 7) / 8) * 8;
   float* part_s = reinterpret_cast<float*>(workspace);

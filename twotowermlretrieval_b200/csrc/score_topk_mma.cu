@@ -5,19 +5,25 @@
 // batched configs (B = 256, 4096).  Per CTA:
 //   * 128 queries (UMMA M = 128), rounded to tf32, live in TENSOR MEMORY as the A operand for
 //     the whole kernel (256 columns), which leaves shared memory to the document stream;
-//   * 32-document tiles (32 KB) stream through a 3-stage TMA ring (SWIZZLE_128B, TFLOAT32 maps:
-//     the copy engine rounds operands to nearest-even); one elected thread issues kind::tf32
-//     MMAs (A from TMEM, B from shared memory) into one of four 32-column TMEM accumulators;
-//   * four epilogue warps: thread = query.  One tcgen05.ld brings the thread its 32 scores;
-//     they are filtered against max(own k-th best, a global lower bound on the k-th best that
-//     all CTAs share through an atomic max) and survivors are appended to the thread's
-//     private 128-slot list in shared memory ([slot][thread] layout, conflict-free).  When a
-//     list could overflow, all 32 lanes of the warp sort their own lists at once with a
-//     data-independent bitonic network (SIMT-parallel, no shuffles) and keep the best k.
-// HBM traffic: N * 1024 B per 128-query pass (document tiles are shared across query tiles
-// through L2 when B > 128).  v1 of this kernel (Q in shared memory, lists in L2, warp-
-// cooperative compaction) spent ~90% of its issue slots in the compaction; see
-// profiles/r1_score_topk_mma_v1_ncu_raw.csv.
+//   * 32-document tiles (32 KB) stream through a 5-stage TMA ring (160 KB in flight per SM:
+//     the measured TMA latency under full HBM load is ~4800 cycles, profiles/r1_*trace*);
+//     TFLOAT32 tensor maps make the copy engine round operands to nearest-even;
+//   * one elected thread issues kind::tf32 MMAs (A from TMEM, B from shared memory, N = 32,
+//     ~23 cycles each, profiles/r1_mma_probe.txt) into one of four TMEM accumulators;
+//   * four epilogue warps, thread = query: one tcgen05.ld brings the thread its 32 scores;
+//     they are filtered against max(own k-th-best bound, a global bound shared by all CTAs
+//     through an atomic max); survivors are appended to the thread's private 128-slot list
+//     (scores in shared memory, [slot][thread] layout; document ids in an L2-resident scratch
+//     with the same layout).  When a list could overflow, the lane finds a pivot with
+//     k <= #(score >= pivot) <= 64 by bisection over the float key space (count passes only:
+//     independent shared-memory loads, no sorting) and compacts in place.
+// The kernel emits unsorted lists of <= 64 candidates per (CTA, query); the merge kernel
+// produces the sorted global top-k.  HBM traffic: N * 1024 B per 128-query pass (document
+// tiles are shared across query tiles through L2 when B > 128).
+//
+// History (profiles/): v1 kept Q in shared memory and lists in L2 with warp-cooperative
+// sorts (90 % of issue slots in the sort); v2/v3 sorted per thread in shared memory (154 k
+// cycles per round, 3 stages: 1850 cycles per tile); this is v4.
 #include <cudaTypedefs.h>
 
 #include "common.cuh"
@@ -27,61 +33,149 @@
 namespace ttr {
 
 int make_tf32_rowmajor_map(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, int box_rows);
+extern int g_debug_flags;   // bits 3-5: timing experiments that break results (skip LDTM / pin the B operand)
 
 constexpr int SM_DIM = 256;
 constexpr int SM_MQ = 128;                 // queries per CTA (UMMA M)
 constexpr int SM_ND = 32;                  // documents per tile (UMMA N)
 constexpr int SM_KB = 8;                   // k-blocks of 32 floats
-constexpr int SM_STAGES = 3;
+constexpr int SM_STAGES = 4;
 constexpr int SM_D_KB_BYTES = SM_ND * 128;              // one k-block of a doc tile: 4 KB
 constexpr int SM_STAGE_BYTES = SM_ND * SM_DIM * 4;      // 32 KB
-constexpr int SM_NACC = 2;                              // TMEM accumulator buffers (tiles in flight)
-constexpr int SM_KSPLIT = 4;                            // independent accumulation chains per tile
-constexpr int SM_ACC_COLS = SM_KSPLIT * SM_ND;          // columns per buffer: 4 partial sums x 32 docs
+constexpr int SM_NACC = 4;                              // TMEM accumulator buffers (tiles in flight)
+constexpr int SM_KSPLIT = 1;                            // accumulation chains per tile (1: no split; the MMA
+                                                        // probe shows dependent chains are not slower)
+constexpr int SM_ACC_COLS = SM_KSPLIT * SM_ND;          // columns per buffer: partial sums x 32 docs
 constexpr int SM_Q_COLS = SM_DIM;                       // A operand: one column per k element
 constexpr int SM_TMEM_COLS = 512;
 constexpr int SM_THREADS = 256;
-constexpr int SM_CAP = TOPK_CAP;                        // candidate slots per query
-constexpr int SM_LIST_BYTES = SM_CAP * SM_MQ * 4;       // one array ([slot][thread]): 64 KB
+constexpr int SM_CAP = 128;                             // candidate slots per query
+constexpr int SM_KEEP = 64;                             // a compaction leaves k..SM_KEEP entries
+constexpr int SM_LIST_BYTES = SM_CAP * SM_MQ * 4;       // score lists ([slot][thread]): 64 KB
+constexpr int SM_LISTI_BYTES = SM_CAP * SM_MQ * 2;      // id lists, uint16 CTA-local document numbers: 32 KB
+constexpr int SM_MAX_TILES_PER_CTA = 65536 / SM_ND;     // so that a local document number fits 16 bits
 
 __device__ __forceinline__ void atomic_max_float(float* addr, float v) {
   if (v >= 0.f) atomicMax(reinterpret_cast<int*>(addr), __float_as_int(v));
   else atomicMin(reinterpret_cast<unsigned int*>(addr), __float_as_uint(v));
 }
 
-// Every lane sorts ITS OWN 128-slot list (descending by (score, idx)); lists are interleaved
-// [slot][thread] so a warp's accesses to one slot are 32 consecutive words.
-__device__ __forceinline__ void thread_sort128_desc(float* ls, int32_t* li) {
-#pragma unroll 1
-  for (int k = 2; k <= SM_CAP; k <<= 1) {
-#pragma unroll 1
-    for (int j = k >> 1; j > 0; j >>= 1) {
-#pragma unroll 4
-      for (int t = 0; t < SM_CAP / 2; ++t) {
-        const int a = ((t & ~(j - 1)) << 1) | (t & (j - 1));
-        const int b = a | j;
-        const bool desc = ((a & k) == 0);
-        const float sa = ls[a * SM_MQ], sb = ls[b * SM_MQ];
-        const int32_t ia = li[a * SM_MQ], ib = li[b * SM_MQ];
-        const bool b_better = key_better<int32_t>(sb, ib, sa, ia);
-        if (b_better == desc) {
-          ls[a * SM_MQ] = sb; ls[b * SM_MQ] = sa;
-          li[a * SM_MQ] = ib; li[b * SM_MQ] = ia;
-        }
+// order-preserving float <-> uint32 key
+__device__ __forceinline__ uint32_t f2key(float f) {
+  const uint32_t b = __float_as_uint(f);
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float key2f(uint32_t k) {
+  return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+
+// Counts of list entries >= each of three pivots in ONE pass (slots >= cnt hold -inf).
+// Two independent accumulator sets and 16 loads in flight: the pass is bound by shared-memory
+// throughput, not by a dependent add chain.
+__device__ __forceinline__ void count_ge3(const float* ls, float p1, float p2, float p3, int& c1, int& c2, int& c3) {
+  int a1 = 0, a2 = 0, a3 = 0, b1 = 0, b2 = 0, b3 = 0;
+#pragma unroll 8
+  for (int e = 0; e < SM_CAP; e += 2) {
+    const float v0 = ls[e * SM_MQ], v1 = ls[(e + 1) * SM_MQ];
+    a1 += v0 >= p1; a2 += v0 >= p2; a3 += v0 >= p3;
+    b1 += v1 >= p1; b2 += v1 >= p2; b3 += v1 >= p3;
+  }
+  c1 = a1 + b1; c2 = a2 + b2; c3 = a3 + b3;
+}
+
+// Per-thread compaction (called by a whole warp; lanes with cnt <= SM_KEEP only tag along).
+// Keeps every entry >= pivot where k <= #kept <= SM_KEEP, or — when a plateau of equal scores
+// straddles that window — the entries above the plateau plus its first (lowest-id) members
+// up to exactly k.  Scores and ids both live in shared memory (an earlier version kept the ids
+// in an L2 scratch: moving them cost ~45 k cycles per round under a saturated memory system).
+// The pivot is searched with three value-space probes per pass (the
+// interval shrinks 4x per pass; ~3 passes on score-like data) and, if that stalls, by
+// bisection over the order-preserving integer keys, which always terminates.
+// Returns the new count; tau = score bound for future candidates, strict = candidates must
+// beat tau strictly (plateau case: later equal scores have larger ids and lose the tie).
+__device__ __forceinline__ int thread_compact(float* ls, uint16_t* li, int cnt, int k, float& tau, bool& strict) {
+  const bool need = cnt > SM_KEEP;
+  for (int e = cnt; e < SM_CAP; ++e) ls[e * SM_MQ] = -INFINITY;      // pads never count
+  float mn = INFINITY, mx = -INFINITY;
+#pragma unroll 8
+  for (int e = 0; e < SM_CAP; ++e) {
+    const float v = ls[e * SM_MQ];
+    if (e < cnt) { mn = fminf(mn, v); mx = fmaxf(mx, v); }
+  }
+  // invariant in key space: count(>= lo) > SM_KEEP, count(>= hi) < k
+  uint32_t lo = f2key(mn), hi = f2key(mx) + 1u;
+  float pivot = mn;
+  bool plateau = false;
+  bool done = !need;
+  int iter = 0;
+  while (__any_sync(0xffffffffu, !done)) {
+    const float flo = key2f(lo), fhi = key2f(hi - 1u);
+    float p1, p2, p3;
+    uint32_t k1, k2, k3;
+    const uint32_t kmid = lo + ((hi - lo) >> 1);
+    p1 = flo + 0.25f * (fhi - flo); p2 = flo + 0.5f * (fhi - flo); p3 = flo + 0.75f * (fhi - flo);
+    k1 = f2key(p1); k2 = f2key(p2); k3 = f2key(p3);
+    const bool value_ok = iter < 10 && k1 > lo && k1 < k2 && k2 < k3 && k3 < hi;
+    if (!value_ok) { k1 = k2 = k3 = kmid; p1 = p2 = p3 = key2f(kmid); }
+    ++iter;
+    int c1, c2, c3;
+    count_ge3(ls, p1, p2, p3, c1, c2, c3);
+    if (!done) {
+      if (hi - lo <= 1u) { plateau = true; pivot = key2f(lo); done = true; }
+      else if (c1 >= k && c1 <= SM_KEEP) { pivot = p1; done = true; }
+      else if (c2 >= k && c2 <= SM_KEEP) { pivot = p2; done = true; }
+      else if (c3 >= k && c3 <= SM_KEEP) { pivot = p3; done = true; }
+      else {
+        // counts are non-increasing in the pivot: tighten both ends
+        if (c3 > SM_KEEP) lo = k3; else if (c2 > SM_KEEP) lo = k2; else if (c1 > SM_KEEP) lo = k1;
+        if (c1 < k) hi = k1; else if (c2 < k) hi = k2; else if (c3 < k) hi = k3;
       }
     }
   }
+  int w = cnt;
+  if (need) {
+    // stable in-place compaction; plateau: keep > pivot, then the first ties until k entries
+    int n_gt = 0;
+    if (plateau) { int d2, d3; const float pg = key2f(lo + 1u); count_ge3(ls, pg, pg, pg, n_gt, d2, d3); }
+    int ties_left = plateau ? (k - n_gt) : 0;
+    w = 0;
+#pragma unroll 1
+    for (int e0 = 0; e0 < SM_CAP; e0 += 8) {
+      if (e0 >= cnt) break;
+      float v[8];
+      uint16_t id[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        v[j] = ls[(e0 + j) * SM_MQ];
+        id[j] = li[(e0 + j) * SM_MQ];
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        bool keep = false;
+        if (e0 + j < cnt) {
+          if (!plateau) keep = v[j] >= pivot;
+          else if (v[j] > pivot) keep = true;
+          else if (v[j] == pivot && ties_left > 0) { keep = true; --ties_left; }
+        }
+        if (keep) { ls[w * SM_MQ] = v[j]; li[w * SM_MQ] = id[j]; ++w; }
+      }
+    }
+    tau = pivot;
+    strict = plateau;
+  }
+  return w;
 }
 
 // Optional timeline trace of CTA (0,0): trace[role][tile] = clock64 at a pipeline event
 // (roles: 0 producer issued, 1 MMA saw full, 2 MMA issued+committed, 3 epilogue saw acc_full,
 // 4 epilogue released the accumulator).  Test/diagnostic only (ttr_debug_set_trace).
 long long* g_score_trace = nullptr;
-constexpr int SM_TRACE_TILES = 256;
+constexpr int SM_TRACE_TILES = 256;   // trace buffer: 8 roles x 256 tiles
 #define SM_TRACE(role, it)                                                                      \
   do {                                                                                          \
-    if (trace && blockIdx.x == 0 && blockIdx.y == 0 && (it) < SM_TRACE_TILES && lane == 0)      \
-      trace[(role) * SM_TRACE_TILES + (it)] = clock64();                                        \
+    const int _ti = (it) - ((dbg & 128) ? 1000 : 0);                                            \
+    if (trace && blockIdx.x == 0 && blockIdx.y == 0 && _ti >= 0 && _ti < SM_TRACE_TILES && lane == 0) \
+      trace[(role) * SM_TRACE_TILES + _ti] = clock64();                                         \
   } while (0)
 
 __global__ void init_tau_kernel(float* tau, int n) {
@@ -89,30 +183,45 @@ __global__ void init_tau_kernel(float* tau, int n) {
   if (i < n) tau[i] = -INFINITY;
 }
 
+// tau[q] = k-th best score of the sample pass (a valid lower bound on the final k-th best)
+__global__ void seed_tau_kernel(float* tau, const float* __restrict__ sample_s, const int64_t* __restrict__ sample_i,
+                                int B, int k) {
+  int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q < B && sample_i[(int64_t)q * k + (k - 1)] >= 0) tau[q] = sample_s[(int64_t)q * k + (k - 1)];
+}
+
+// Scratch layout per CTA c = slice * n_qt + qt (thread ql = query inside the tile):
+//   out_s  [c][slot][ql] fp32   final candidate scores        (slot < SM_KEEP)
+//   out_i  [c][slot][ql] i32    final candidate ids
+//   out_n  [c][ql] i32          final count
 __global__ void __launch_bounds__(SM_THREADS, 1)
 score_topk_mma_kernel(const float* __restrict__ Q, const __grid_constant__ CUtensorMap map_d, int B, int64_t N,
-                      int k, int n_slices, float* __restrict__ tau_g, float* __restrict__ part_s,
-                      int32_t* __restrict__ part_i, long long* __restrict__ trace) {
+                      int k, int n_slices, float* __restrict__ tau_g, float* __restrict__ out_s,
+                      int32_t* __restrict__ out_i, int32_t* __restrict__ out_n, long long* __restrict__ trace,
+                      int dbg) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* base = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
   unsigned char* ring = base;                                      // [stages][SM_KB][32 rows][128 B]
   float* list_s = reinterpret_cast<float*>(ring + SM_STAGES * SM_STAGE_BYTES);   // [SM_CAP][128]
-  int32_t* list_i = reinterpret_cast<int32_t*>(reinterpret_cast<unsigned char*>(list_s) + SM_LIST_BYTES);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(list_i) + SM_LIST_BYTES);
+  uint16_t* list_i = reinterpret_cast<uint16_t*>(reinterpret_cast<unsigned char*>(list_s) + SM_LIST_BYTES);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(list_i) + SM_LISTI_BYTES);
   uint64_t* empty_bar = full_bar + SM_STAGES;
   uint64_t* acc_full = empty_bar + SM_STAGES;
   uint64_t* acc_empty = acc_full + SM_NACC;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + SM_NACC);
+  __shared__ uint64_t probe_bar;             // dbg & 64: the MMA warp waits for its own commit (timing experiment)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qt = blockIdx.x;                 // query tile
   const int slice = blockIdx.y;              // document slice
   const int q0 = qt * SM_MQ;
   const int64_t n_tiles = ceil_div64(N, (int64_t)SM_ND);
+  const int cta = slice * gridDim.x + qt;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < SM_STAGES; ++s) { ptx::mbar_init(full_bar + s, 1); ptx::mbar_init(empty_bar + s, 1); }
     for (int b = 0; b < SM_NACC; ++b) { ptx::mbar_init(acc_full + b, 1); ptx::mbar_init(acc_empty + b, 4); }
+    ptx::mbar_init(&probe_bar, 1);
     ptx::fence_mbar_init();
   }
   if (warp == 2) {
@@ -181,28 +290,34 @@ score_topk_mma_kernel(const float* __restrict__ Q, const __grid_constant__ CUten
       ptx::mbar_wait(full_bar + s, ph);
       ptx::tc_fence_after_sync();
       SM_TRACE(1, it);
-      const uint32_t d_addr = ptx::smem_u32(ring + s * SM_STAGE_BYTES);
+      const uint32_t d_addr = ptx::smem_u32(ring + ((dbg & 16) ? 0 : s) * SM_STAGE_BYTES);
       const uint32_t d_tmem = tmem_acc + buf * SM_ACC_COLS;
       const uint64_t b_desc0 = ptx::make_kmajor_sw128_desc(d_addr);
       if (ptx::elect_one()) {
-        // The K = 256 reduction is split into SM_KSPLIT independent accumulation chains
-        // (k-steps [c*8, c*8+8) -> partial accumulator c) issued round-robin so consecutive
-        // MMAs never depend on each other; the epilogue adds the partial sums.
+        // Measured (profiles/r1_score_topk_mma_v3_trace_b16.txt vs v4): one accumulation chain
+        // per tile runs at ~2950 cycles per tile, four interleaved chains at <= 1850, so the
+        // K = 256 reduction is split into SM_KSPLIT partial accumulators (k-steps
+        // [c*8, c*8+8) -> accumulator c) issued round-robin; the epilogue adds them.
 #pragma unroll
         for (int kk = 0; kk < 32 / SM_KSPLIT; ++kk) {
 #pragma unroll
           for (int c = 0; c < SM_KSPLIT; ++c) {
             const int ks = c * (32 / SM_KSPLIT) + kk;              // k-step 0..31 (8 floats each)
             // k-block (ks>>2) starts (ks>>2)*4 KB further (>>4 in descriptor units); 32 B per k-step inside it
-            const uint64_t b_desc = b_desc0 + (uint64_t)((ks >> 2) * (SM_D_KB_BYTES >> 4) + 2 * (ks & 3));
+            const uint64_t b_desc = b_desc0 + (uint64_t)(((dbg & 32) ? 0 : (ks >> 2)) * (SM_D_KB_BYTES >> 4) + 2 * (ks & 3));
             ptx::mma_tf32_ts(d_tmem + c * SM_ND, tmem_base + ks * 8, b_desc, idesc, kk != 0);
           }
         }
         ptx::mma_commit(empty_bar + s);
         ptx::mma_commit(acc_full + buf);
+        if (dbg & 64) ptx::mma_commit(&probe_bar);
       }
       __syncwarp();
       SM_TRACE(2, it);
+      if (dbg & 64) {
+        ptx::mbar_wait(&probe_bar, (uint32_t)it & 1u);
+        SM_TRACE(5, it);
+      }
     }
   } else if (warp >= 4) {
     // ===== epilogue: one thread per query =====
@@ -211,15 +326,14 @@ score_topk_mma_kernel(const float* __restrict__ Q, const __grid_constant__ CUten
     const int q = q0 + ql;
     const bool q_valid = q < B;
     float* ls = list_s + ql;
-    int32_t* li = list_i + ql;
-    float tau_s = -INFINITY;
-    int32_t tau_i = IDX_PAD;
+    uint16_t* li = list_i + ql;   // CTA-local document number: it * 32 + j
+    float tau = -INFINITY;                     // own bound on the k-th best
+    bool strict = false;
     int cnt = 0;
     int it = 0;
     // Global lower bound on the k-th best.  An L2 read under a saturated memory system costs
-    // microseconds, so it is refreshed every 8 tiles and consumed one refresh later (the load
-    // is in flight for 8 tiles and never sits on the per-tile critical path).
-    float tg = q_valid ? -INFINITY : INFINITY;
+    // microseconds, so it is refreshed every 8 tiles and consumed one refresh later.
+    float tg = q_valid ? __ldcg(tau_g + q) : INFINITY;     // seeded by the sample pass (or -inf)
     float tg_pending = tg;
     for (int64_t t = slice; t < n_tiles; t += n_slices, ++it) {
       const int buf = it % SM_NACC;
@@ -235,12 +349,17 @@ score_topk_mma_kernel(const float* __restrict__ Q, const __grid_constant__ CUten
       {
         uint32_t r[32];
         const uint32_t tcol = tmem_acc + ((uint32_t)(qw * 32) << 16) + buf * SM_ACC_COLS;
-        ptx::tmem_ld_32x32(tcol, r);
-        ptx::tmem_ld_wait();
+        if (!(dbg & 8)) {
+          ptx::tmem_ld_32x32(tcol, r);
+          ptx::tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) r[j] = 0;
+        }
 #pragma unroll
         for (int j = 0; j < 32; ++j) sc32[j] = __uint_as_float(r[j]);
 #pragma unroll
-        for (int c = 1; c < SM_KSPLIT; ++c) {
+        for (int c = 1; c < ((dbg & 8) ? 1 : SM_KSPLIT); ++c) {
           ptx::tmem_ld_32x32(tcol + c * SM_ND, r);
           ptx::tmem_ld_wait();
 #pragma unroll
@@ -252,41 +371,58 @@ score_topk_mma_kernel(const float* __restrict__ Q, const __grid_constant__ CUten
       if (lane == 0) ptx::mbar_arrive(acc_empty + buf);
       if (qw == 0) SM_TRACE(4, it);
       const int64_t d0 = t * SM_ND;
-      const float thr = fmaxf(tg, tau_s);
+      // one threshold, one compare per score: "strictly above tau" == ">= next float above tau"
+      const float thr = fmaxf(tg, strict ? key2f(f2key(tau) + 1u) : tau);
+      // Branch-free filter -> per-lane bit mask of surviving documents.  (A short-circuit
+      // condition compiles to a branch per score: ~45 cycles of resolve latency each with one
+      // warp per scheduler, 1300-1600 cycles per tile; profiles/r1_score_topk_mma_v4_trace_*.)
+      uint32_t mask = 0;
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const float sc = sc32[j];
-        if (sc >= thr) {
-          const int64_t doc = d0 + j;
-          if (doc < N && key_better<int32_t>(sc, (int32_t)doc, tau_s, tau_i)) {
-            ls[cnt * SM_MQ] = sc;
-            li[cnt * SM_MQ] = (int32_t)doc;
-            ++cnt;
-          }
+      for (int j = 0; j < 32; ++j) mask |= (sc32[j] >= thr ? 1u : 0u) << j;
+      // the tail tile: documents >= N are zero-filled by TMA and must not count
+      if (d0 + 32 > N) mask &= (N - d0 >= 32) ? 0xffffffffu : ((1u << (int)(N - d0)) - 1u);
+      // Visit only the documents that survive in SOME lane (warp-uniform loop over the OR of
+      // the lane masks, usually 0-2 bits): traversing 32 conditional regions costs ~1500 cycles
+      // per tile even when nothing is appended (profiles/r1_score_topk_mma_v4_trace_*).
+      uint32_t any_mask = __reduce_or_sync(0xffffffffu, mask);
+      while (any_mask) {
+        const int j = __ffs(any_mask) - 1;
+        any_mask &= any_mask - 1u;
+        float scj = 0.f;
+        switch (j) {   // j is warp-uniform: a uniform jump selects the register
+#define SM_CASE(J) case J: scj = sc32[J]; break;
+          SM_CASE(0) SM_CASE(1) SM_CASE(2) SM_CASE(3) SM_CASE(4) SM_CASE(5) SM_CASE(6) SM_CASE(7)
+          SM_CASE(8) SM_CASE(9) SM_CASE(10) SM_CASE(11) SM_CASE(12) SM_CASE(13) SM_CASE(14) SM_CASE(15)
+          SM_CASE(16) SM_CASE(17) SM_CASE(18) SM_CASE(19) SM_CASE(20) SM_CASE(21) SM_CASE(22) SM_CASE(23)
+          SM_CASE(24) SM_CASE(25) SM_CASE(26) SM_CASE(27) SM_CASE(28) SM_CASE(29) SM_CASE(30) SM_CASE(31)
+#undef SM_CASE
+        }
+        if ((mask >> j) & 1u) {   // cnt <= SM_CAP - SM_ND before the tile, so 32 free slots exist
+          ls[cnt * SM_MQ] = scj;
+          li[cnt * SM_MQ] = (uint16_t)(it * SM_ND + j);
+          ++cnt;
         }
       }
+      if (qw == 0) SM_TRACE(6, it);
       if (__any_sync(0xffffffffu, cnt > SM_CAP - SM_ND)) {
-        // all 32 lanes compact their own list together (uniform control flow)
-        for (int e = cnt; e < SM_CAP; ++e) { ls[e * SM_MQ] = -INFINITY; li[e * SM_MQ] = IDX_PAD; }
-        thread_sort128_desc(ls, li);
-        if (cnt >= k) {
-          cnt = k;
-          tau_s = ls[(k - 1) * SM_MQ];
-          tau_i = li[(k - 1) * SM_MQ];
-          if (q_valid) atomic_max_float(tau_g + q, tau_s);
-        }
+        __syncwarp();
+        cnt = thread_compact(ls, li, cnt, k, tau, strict);
+        if (q_valid && cnt >= k) atomic_max_float(tau_g + q, tau);
       }
+      if (qw == 0) SM_TRACE(7, it);
     }
-    // final sort, then emit this CTA's partial list for the query
-    for (int e = cnt; e < SM_CAP; ++e) { ls[e * SM_MQ] = -INFINITY; li[e * SM_MQ] = IDX_PAD; }
-    thread_sort128_desc(ls, li);
-    if (q_valid) {
-      const int64_t pbase = ((int64_t)q * n_slices + slice) * k;
-      for (int e = 0; e < k; ++e) {
-        part_s[pbase + e] = ls[e * SM_MQ];
-        part_i[pbase + e] = li[e * SM_MQ];
+    // final: leave at most SM_KEEP candidates, publish scores + count (ids stay in the scratch)
+    __syncwarp();
+    if (__any_sync(0xffffffffu, cnt > SM_KEEP)) cnt = thread_compact(ls, li, cnt, k, tau, strict);
+    float* os = out_s + ((size_t)cta * SM_KEEP) * SM_MQ + ql;
+    int32_t* oi = out_i + ((size_t)cta * SM_KEEP) * SM_MQ + ql;
+    for (int e = 0; e < SM_KEEP; ++e)
+      if (e < cnt) {
+        const int lid = li[e * SM_MQ];                       // local -> global: tile = slice + it * n_slices
+        os[e * SM_MQ] = ls[e * SM_MQ];
+        oi[e * SM_MQ] = (int32_t)(((int64_t)slice + (int64_t)(lid >> 5) * n_slices) * SM_ND + (lid & 31));
       }
-    }
+    out_n[cta * SM_MQ + ql] = q_valid ? cnt : 0;
   }
 
   ptx::tc_fence_before_sync();
@@ -294,51 +430,140 @@ score_topk_mma_kernel(const float* __restrict__ Q, const __grid_constant__ CUten
   if (warp == 2) ptx::tmem_dealloc(tmem_base, SM_TMEM_COLS);
 }
 
+// One CTA per query: gather the <= SM_KEEP candidates of every document slice, exact top-k.
+__global__ void __launch_bounds__(256)
+topk_merge_tiled_kernel(const float* __restrict__ out_s, const int32_t* __restrict__ out_i,
+                        const int32_t* __restrict__ out_n, int n_qt, int n_slices, int k, int64_t idx_offset,
+                        float* __restrict__ res_s, int64_t* __restrict__ res_i) {
+  __shared__ float buf_s[8][TOPK_CAP];
+  __shared__ int32_t buf_i[8][TOPK_CAP];
+  __shared__ int cnts[8];
+  __shared__ float mrg_s[8 * TOPK_KMAX];
+  __shared__ int32_t mrg_i[8 * TOPK_KMAX];
+  const int q = blockIdx.x;
+  const int qt = q / SM_MQ, ql = q % SM_MQ;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float tau_s = -INFINITY;
+  int32_t tau_i = IDX_PAD;
+  int cnt = 0;
+  const int total = n_slices * SM_KEEP;
+  for (int t0 = warp * 32; t0 < total; t0 += 256) {
+    const int t = t0 + lane;
+    float s = -INFINITY;
+    int32_t ix = IDX_PAD;
+    if (t < total) {
+      const int slice = t / SM_KEEP, e = t % SM_KEEP;
+      const int cta = slice * n_qt + qt;
+      if (e < out_n[cta * SM_MQ + ql]) {
+        s = out_s[((size_t)cta * SM_KEEP + e) * SM_MQ + ql];
+        ix = out_i[((size_t)cta * SM_KEEP + e) * SM_MQ + ql];
+      }
+    }
+    const bool pass = ix != IDX_PAD && key_better<int32_t>(s, ix, tau_s, tau_i);
+    const unsigned m = __ballot_sync(0xffffffffu, pass);
+    if (m) {
+      if (pass) {
+        int pos = cnt + __popc(m & ((1u << lane) - 1));
+        buf_s[warp][pos] = s;
+        buf_i[warp][pos] = ix;
+      }
+      cnt += __popc(m);
+      __syncwarp();
+      if (cnt > TOPK_CAP - 32) {
+        cnt = warp_compact<int32_t>(buf_s[warp], buf_i[warp], cnt, k, lane, tau_s, tau_i);
+        __syncwarp();
+      }
+    }
+  }
+  cnt = warp_compact<int32_t>(buf_s[warp], buf_i[warp], cnt, k, lane, tau_s, tau_i);
+  if (lane == 0) cnts[warp] = cnt;
+  __syncthreads();
+  for (int t = threadIdx.x; t < 8 * TOPK_KMAX; t += blockDim.x) {
+    int w = t / TOPK_KMAX, j = t % TOPK_KMAX;
+    bool valid = j < cnts[w];
+    mrg_s[t] = valid ? buf_s[w][j] : -INFINITY;
+    mrg_i[t] = valid ? buf_i[w][j] : IDX_PAD;
+  }
+  __syncthreads();
+  block_bitonic_desc<int32_t>(mrg_s, mrg_i, 8 * TOPK_KMAX);
+  for (int j = threadIdx.x; j < k; j += blockDim.x) {
+    const bool valid = mrg_i[j] != IDX_PAD;
+    res_s[(int64_t)q * k + j] = mrg_s[j];
+    res_i[(int64_t)q * k + j] = valid ? (int64_t)mrg_i[j] + idx_offset : (int64_t)-1;
+  }
+}
+
 struct MmaPlan {
-  int n_qt, n_slices;
-  int64_t tau_off, part_s_off, part_i_off, total;
+  int n_qt, n_slices, n_ctas;
+  int64_t tau_off, outs_off, outi_off, outn_off, total;
 };
 
-MmaPlan mma_plan(int B, int k) {
+MmaPlan mma_plan(int B, int64_t N) {
   MmaPlan p;
   p.n_qt = ceil_div(B, SM_MQ);
   const int sms = sm_count();
   p.n_slices = std::max(1, sms / p.n_qt);      // one wave: n_qt * n_slices <= #SMs (1 CTA per SM)
+  // a CTA numbers its documents with 16 bits: at most 65536 documents (2048 tiles) per slice
+  const int64_t n_tiles = ceil_div64(N, (int64_t)SM_ND);
+  p.n_slices = (int)std::max<int64_t>(p.n_slices, ceil_div64(n_tiles, (int64_t)SM_MAX_TILES_PER_CTA));
+  p.n_ctas = p.n_qt * p.n_slices;
+  auto align = [](int64_t v) { return (v + 255) / 256 * 256; };
   const int64_t bp = (int64_t)p.n_qt * SM_MQ;
   p.tau_off = 0;
-  p.part_s_off = (bp * 4 + 255) / 256 * 256;
-  const int64_t part_elems = bp * p.n_slices * k;
-  p.part_i_off = p.part_s_off + part_elems * 4;
-  p.total = p.part_i_off + part_elems * 4 + 256;
+  p.outs_off = align(bp * 4);
+  p.outi_off = align(p.outs_off + (int64_t)p.n_ctas * SM_KEEP * SM_MQ * 4);
+  p.outn_off = align(p.outi_off + (int64_t)p.n_ctas * SM_KEEP * SM_MQ * 4);
+  p.total = align(p.outn_off + (int64_t)p.n_ctas * SM_MQ * 4);
   return p;
 }
 
-int launch_score_topk_mma(const float* Q, int B, const float* docs, int64_t N, int k, void* workspace,
-                          float** part_s_out, int32_t** part_i_out, int* parts_out, cudaStream_t st) {
-  MmaPlan p = mma_plan(B, k);
+int launch_score_topk_mma(const float* Q, int B, const float* docs, int64_t N, int k, int64_t row_offset,
+                          void* workspace, float* out_scores, int64_t* out_idx, cudaStream_t st) {
+  MmaPlan p = mma_plan(B, N);
   unsigned char* ws = reinterpret_cast<unsigned char*>(workspace);
   float* tau = reinterpret_cast<float*>(ws + p.tau_off);
-  float* part_s = reinterpret_cast<float*>(ws + p.part_s_off);
-  int32_t* part_i = reinterpret_cast<int32_t*>(ws + p.part_i_off);
-  CUtensorMap map_d;
-  int rc = make_tf32_rowmajor_map(&map_d, docs, N, SM_DIM, SM_ND);
-  if (rc != TTR_OK) return rc;
+  float* outs = reinterpret_cast<float*>(ws + p.outs_off);
+  int32_t* outi = reinterpret_cast<int32_t*>(ws + p.outi_off);
+  int32_t* outn = reinterpret_cast<int32_t*>(ws + p.outn_off);
   const int nq_pad = p.n_qt * SM_MQ;
   init_tau_kernel<<<ceil_div(nq_pad, 256), 256, 0, st>>>(tau, nq_pad);
   TTR_CHECK_LAUNCH();
-  const size_t smem = (size_t)SM_STAGES * SM_STAGE_BYTES + 2 * SM_LIST_BYTES + (2 * SM_STAGES + 2 * SM_NACC) * 8 + 16 + 1024;
+  const size_t smem = (size_t)SM_STAGES * SM_STAGE_BYTES + SM_LIST_BYTES + SM_LISTI_BYTES + (2 * SM_STAGES + 2 * SM_NACC) * 8 + 16 + 1024;
   TTR_CHECK_CUDA(cudaFuncSetAttribute(score_topk_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  // Sample pass: exact top-k of the first ~38 k documents gives every query a k-th-best bound
+  // (top ~0.1 %) before the full scan starts.  Without it each CTA spends its first ~250
+  // tiles appending and compacting almost everything it sees (3-4 k cycles per tile instead
+  // of ~1.2 k; profiles/r1_score_topk_mma_v4_trace_*).  The bound is valid for any document
+  // order; its tightness only matters for speed.
+  const int64_t n_sample = (int64_t)sm_count() * 8 * SM_ND;
+  if (N >= 8 * n_sample && !(g_debug_flags & 256)) {
+    MmaPlan ps = mma_plan(B, n_sample);
+    CUtensorMap map_s;
+    int rc = make_tf32_rowmajor_map(&map_s, docs, n_sample, SM_DIM, SM_ND);
+    if (rc != TTR_OK) return rc;
+    dim3 gs(ps.n_qt, ps.n_slices);
+    score_topk_mma_kernel<<<gs, SM_THREADS, smem, st>>>(Q, map_s, B, n_sample, k, ps.n_slices, tau, outs, outi, outn,
+                                                       nullptr, g_debug_flags);
+    TTR_CHECK_LAUNCH();
+    topk_merge_tiled_kernel<<<B, 256, 0, st>>>(outs, outi, outn, ps.n_qt, ps.n_slices, k, 0, out_scores, out_idx);
+    TTR_CHECK_LAUNCH();
+    seed_tau_kernel<<<ceil_div(B, 256), 256, 0, st>>>(tau, out_scores, out_idx, B, k);
+    TTR_CHECK_LAUNCH();
+  }
+  CUtensorMap map_d;
+  int rc = make_tf32_rowmajor_map(&map_d, docs, N, SM_DIM, SM_ND);
+  if (rc != TTR_OK) return rc;
   dim3 grid(p.n_qt, p.n_slices);
-  score_topk_mma_kernel<<<grid, SM_THREADS, smem, st>>>(Q, map_d, B, N, k, p.n_slices, tau, part_s, part_i,
-                                                        g_score_trace);
+  score_topk_mma_kernel<<<grid, SM_THREADS, smem, st>>>(Q, map_d, B, N, k, p.n_slices, tau, outs, outi, outn,
+                                                        g_score_trace, g_debug_flags);
   TTR_CHECK_LAUNCH();
-  *part_s_out = part_s;
-  *part_i_out = part_i;
-  *parts_out = p.n_slices;
+  topk_merge_tiled_kernel<<<B, 256, 0, st>>>(outs, outi, outn, p.n_qt, p.n_slices, k, row_offset, out_scores,
+                                            out_idx);
+  TTR_CHECK_LAUNCH();
   return TTR_OK;
 }
 
-int64_t score_topk_mma_workspace_bytes(int B, int k) { return mma_plan(B, k).total; }
+int64_t score_topk_mma_workspace_bytes(int B, int64_t N) { return mma_plan(B, N).total; }
 
 }  // namespace ttr
 
