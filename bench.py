@@ -42,7 +42,7 @@ def parse():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--batch", type=int, default=8, help="queries per step")
+    ap.add_argument("--batch", type=int, default=128, help="queries per step")
     ap.add_argument("--docs", type=int, default=N_DOCS)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-extra", action="store_true", help="skip the secondary measurements")
@@ -256,7 +256,7 @@ def run_b200(args):
 
     hbm_peak, peak_src, _ = peaks()
     shard_rows = hi - lo
-    # B <= 8: CUDA-core streaming kernel, one pass; B > 8: tcgen05 kernel, one HBM pass per call
+    # B <= 4: CUDA-core streaming kernel, one pass; B > 4: tcgen05 kernel, one HBM pass per call
     # (query tiles of 128 share document tiles through L2)
     passes = 1
     algo_bytes = shard_rows * BYTES_PER_DOC * passes     # per search call on this rank
@@ -268,10 +268,10 @@ def run_b200(args):
         "config": bench_config(args, world),
         "e2e": {"value": B / (ms_e2e * 1e-3), "unit": "queries/s", "h2d_bytes_per_step": B * DIM * 4,
                 "d2h_bytes_per_step": B * TOPK * 12, "ms_per_step": ms_e2e},
-        "gpu_launches": K * ((1 if B <= 8 else 2) + 1 + (1 if world > 1 else 0)),
+        "gpu_launches": K * ((2 if B <= 4 else 6) + (1 if world > 1 else 0)),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                      "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
-                     "kernel": ("score_topk_stream_kernel" if B <= 8 else "score_topk_mma_kernel") +
+                     "kernel": ("score_topk_stream_kernel" if B <= 4 else "score_topk_mma_kernel") +
                                " (+ topk_merge_kernel, ~1% of the call)",
                      "algorithmic_bytes_per_call": algo_bytes, "ms_per_call": ms_kern,
                      "passes_over_shard_per_call": passes},

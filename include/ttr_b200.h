@@ -161,8 +161,8 @@ int ttr_clip_adam(float* params, const float* grads, float* exp_avg, float* exp_
  * materialises [B, N].
  * Q fp32 [B, D]; docs fp32 [N, D] row-major (the document_embeddings.npy layout,
  * backend/main.py:138); D must be 256 for the fused kernels; k <= 64.
- * B <= 8: CUDA-core streaming kernel (fp32 exact products, HBM-bound);
- * B  > 8: tcgen05 kind::tf32 kernel, 128 queries per pass (scores within 1e-3 relative).
+ * B <= 4: CUDA-core streaming kernel (fp32 exact products, HBM-bound);
+ * B  > 4: tcgen05 kind::tf32 kernel, 128 queries per pass (scores within 1e-3 relative).
  * row_offset is added to the emitted indices (global ids of a row shard).
  * out_scores fp32 [B, k] descending; out_idx int64 [B, k]; ties: lower index first.
  * workspace: ttr_score_topk_workspace_bytes(B, N, k) bytes. */

@@ -1,0 +1,115 @@
+"""GPU, 2 ranks (needs >= 2 devices; skipped otherwise): row-sharded search / hybrid rerank
+over NCCL == single-device result, and data-parallel training == single-device training on the
+concatenated batch (the all-reduce + fused clip/Adam path)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        from twotowermlretrieval_b200 import TwoTowerModel, synth, triplet_loss_cosine
+        from twotowermlretrieval_b200.index import CsrF64, ShardedIndex, hybrid_rerank, search_topk, shard_bounds
+        from twotowermlretrieval_b200.optim import FusedClipAdam
+        out = {}
+        # ---- sharded search + hybrid
+        N, F = 30011, 300
+        D = torch.tensor(synth.make_unit_rows(N, 256, seed=3), device=dev)
+        indptr, indices, data = synth.make_tfidf_csr(N, n_features=F, mean_nnz=8, seed=2)
+        full_csr = CsrF64.from_arrays(indptr, indices, data, dev)
+        lo, hi = shard_bounds(N, world, rank)
+        idx = ShardedIndex(D[lo:hi].contiguous(), lo, N, tfidf_local=full_csr.row_slice(lo, hi))
+        qptr = np.arange(0, 4 * 5 + 1, 4)
+        rng = np.random.default_rng(1)
+        qidx = np.concatenate([np.sort(rng.choice(F, 4, replace=False)) for _ in range(5)])
+        qcsr = CsrF64.from_arrays(qptr, qidx, np.full(20, 0.5), dev)
+        for B in (3, 40):
+            Q = torch.tensor(synth.make_unit_rows(B, 256, seed=40 + B), device=dev)
+            s, i = idx.search(Q, 50)
+            s1, i1 = search_topk(Q, D, 50)
+            out[f"search{B}"] = bool(torch.equal(i, i1) and torch.allclose(s, s1, atol=1e-6))
+        Q = torch.tensor(synth.make_unit_rows(5, 256, seed=9), device=dev)
+        h = idx.search_hybrid(Q, qcsr, alpha=0.4, k=50, top_n=10)
+        s1, i1 = search_topk(Q, D, 50)
+        h1 = hybrid_rerank(i1, s1, 0.4, docs_csr=full_csr, q_csr=qcsr, top_n=10)
+        out["hybrid"] = bool(torch.equal(h["idx"], h1["idx"]) and torch.equal(h["final"], h1["final"]))
+        # ---- data-parallel training step: 2 ranks x 8 triplets == 1 rank x 16 triplets
+        cfg = synth.default_config(vocab_size=3000, embed_dim=200)
+        cfg["DROPOUT"] = 0.0
+        sd = synth.make_state_dict(cfg, seed=0, table_seed=1)
+        q_ids, _ = synth.make_tokens(16, "query", 3000, seed=11)
+        p_ids, _ = synth.make_tokens(16, "passage", 3000, seed=12, lengths=np.random.default_rng(12).integers(8, 30, 16))
+        n_ids, _ = synth.make_tokens(16, "passage", 3000, seed=13, lengths=np.random.default_rng(13).integers(8, 30, 16))
+
+        def run(sl, group_world):
+            m = TwoTowerModel(cfg, sd["query_encoder.embedding.weight"])
+            m.load_state_dict({k: torch.tensor(v) for k, v in sd.items()})
+            m.to(dev).train()
+            opt = FusedClipAdam(m, lr=1e-3, max_norm=1.0)
+            if group_world == 1:
+                opt.group = dist.new_group([rank])      # single-rank group: no exchange
+            for _ in range(2):
+                opt.zero_grad()
+                loss = triplet_loss_cosine((m.encode_query(torch.tensor(q_ids[sl], device=dev)),
+                                            m.encode_document(torch.tensor(p_ids[sl], device=dev)),
+                                            m.encode_document(torch.tensor(n_ids[sl], device=dev))), margin=0.5)
+                loss.backward()
+                opt.step()
+            return m.flat_params().clone(), float(opt.last_grad_norm)
+
+        # new_group must be called by all ranks for every group
+        groups = [dist.new_group([r]) for r in range(world)]
+        m_dp = TwoTowerModel(cfg, sd["query_encoder.embedding.weight"])
+        m_dp.load_state_dict({k: torch.tensor(v) for k, v in sd.items()})
+        m_dp.to(dev).train()
+        opt_dp = FusedClipAdam(m_dp, lr=1e-3, max_norm=1.0)
+        sl = slice(rank * 8, rank * 8 + 8)
+        m_one = TwoTowerModel(cfg, sd["query_encoder.embedding.weight"])
+        m_one.load_state_dict({k: torch.tensor(v) for k, v in sd.items()})
+        m_one.to(dev).train()
+        opt_one = FusedClipAdam(m_one, lr=1e-3, max_norm=1.0, process_group=groups[rank])
+        for _ in range(2):
+            for m, opt, s_ in ((m_dp, opt_dp, sl), (m_one, opt_one, slice(0, 16))):
+                opt.zero_grad()
+                loss = triplet_loss_cosine((m.encode_query(torch.tensor(q_ids[s_], device=dev)),
+                                            m.encode_document(torch.tensor(p_ids[s_], device=dev)),
+                                            m.encode_document(torch.tensor(n_ids[s_], device=dev))), margin=0.5)
+                loss.backward()
+                opt.step()
+        a, b = m_dp.flat_params(), m_one.flat_params()
+        out["dp_max_param_diff"] = float((a - b).abs().max())
+        out["dp_norms"] = (float(opt_dp.last_grad_norm), float(opt_one.last_grad_norm))
+        torch.cuda.synchronize()
+        q.put((rank, out))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_sharded_search_hybrid_and_dp_training():
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29600 + (os.getpid() % 1000)
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    [p.start() for p in procs]
+    res = dict(q.get(timeout=600) for _ in range(2))
+    [p.join(120) for p in procs]
+    for rank in (0, 1):
+        r = res[rank]
+        assert r["search3"] and r["search40"] and r["hybrid"], r
+        # mean-of-means over equal shards == mean over the global batch; clip + Adam identical up to fp32
+        # reduction order.  Two Adam steps at lr=1e-3 move every weight by ~1e-3 each; elements whose
+        # gradient is ~eps may differ by a few percent of that.
+        assert r["dp_max_param_diff"] < 1e-4, r
+        assert abs(r["dp_norms"][0] - r["dp_norms"][1]) < 1e-3 * r["dp_norms"][1], r

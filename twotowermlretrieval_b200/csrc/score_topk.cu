@@ -7,7 +7,7 @@
 // (values are scattered across lanes instead of all-reduced, 5 shuffle rounds in total),
 // and filters scores against a per-(warp,query) running k-th best held in shared memory.
 // The [B, N] score matrix is never written.  Algorithmic traffic: N * 1024 B per pass.
-// (Batches > 8 go to the tcgen05 kernel in score_topk_mma.cu; debug flag bit 2 forces this
+// (Batches > 4 go to the tcgen05 kernel in score_topk_mma.cu; debug flag bit 2 forces this
 // kernel for any batch so the tests can compare the two paths.)
 #include "ptx.cuh"
 #include "topk_common.cuh"
@@ -319,9 +319,10 @@ int launch_score_topk_mma(const float* Q, int B, const float* docs, int64_t N, i
                           void* workspace, float* out_scores, int64_t* out_idx, cudaStream_t st);
 int64_t score_topk_mma_workspace_bytes(int B, int64_t N);
 
-// Query batches up to this size run the CUDA-core streaming kernel (HBM-bound up to ~4
-// queries per pass); larger batches run the tcgen05 kernel (128 queries per pass).
-constexpr int STREAM_MAX_B = 8;
+// Query batches up to this size run the CUDA-core streaming kernel (exact fp32 products,
+// HBM-bound up to 4 queries per pass; 8 queries are fp32-FMA-bound at 2.5 ms vs 1.5 ms for the
+// tensor-core path); larger batches run the tcgen05 kernel (128 queries per pass).
+constexpr int STREAM_MAX_B = 4;
 
 }  // namespace ttr
 

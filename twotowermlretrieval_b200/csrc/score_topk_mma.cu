@@ -1,4 +1,4 @@
-// score_topk_mma.cu — exact cosine top-k for query batches > 8: tcgen05 score GEMM fused
+// score_topk_mma.cu — exact cosine top-k for query batches > 4: tcgen05 score GEMM fused
 // with a per-query streaming top-k, never materialising [B, N].
 //
 // Replaces `torch.matmul(q, D.t())` + `torch.topk` (backend/evaluators.py:185-186) for the
