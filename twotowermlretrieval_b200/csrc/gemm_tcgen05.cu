@@ -24,17 +24,19 @@ constexpr int G_STAGE_BYTES = G_A_BYTES + G_B_BYTES;
 constexpr int G_ACC_COLS = GN;           // fp32 accumulator columns per buffer
 constexpr int G_TMEM_COLS = 2 * G_ACC_COLS;
 constexpr int G_THREADS = 256;
+constexpr int G_OUT_BYTES = GM * 32 * 4;   // staging buffer of one 128 x 32 output chunk: 16 KB (x2)
 
 extern int g_debug_flags;
 
 __global__ void __launch_bounds__(G_THREADS, 1)
 gemm_tf32_bias_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
-                      const float* __restrict__ bias, float* __restrict__ C, int m_bound,
+                      const __grid_constant__ CUtensorMap map_c, const float* __restrict__ bias, int m_bound,
                       const int32_t* __restrict__ m_valid, int N, int K) {
   extern __shared__ unsigned char smem_raw[];
   // [stages][A | B]; SWIZZLE_128B atoms need 1024-byte alignment in the shared window
   unsigned char* tiles = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(tiles + G_STAGES * G_STAGE_BYTES);
+  unsigned char* out_stage = tiles + G_STAGES * G_STAGE_BYTES;      // [2][128 rows][128 B], SWIZZLE_128B
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(out_stage + 2 * G_OUT_BYTES);
   uint64_t* empty_bar = full_bar + G_STAGES;
   uint64_t* acc_full = empty_bar + G_STAGES;    // [2] MMA -> epilogue
   uint64_t* acc_empty = acc_full + 2;           // [2] epilogue -> MMA
@@ -113,45 +115,56 @@ gemm_tf32_bias_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
       }
     }
   } else if (warp >= 4) {
-    // ===== epilogue: TMEM -> registers -> (+bias) -> global =====
+    // ===== epilogue: TMEM -> registers (+bias) -> swizzled smem staging -> TMA store =====
+    // (per-thread row stores hit 32 different 6 KB-strided rows per instruction and ran the
+    // output at 1.1 TB/s, profiles/r1_encode_breakdown_v1.txt; the copy engine writes whole
+    // 128-byte row segments.)  Rows between the valid count and m_bound are written too; they
+    // belong to the caller's buffer and are never read.
     const int q = warp - 4;                               // TMEM lane quadrant of this warp
-    int local = 0;
+    const int r_in_tile = q * 32 + lane;
+    int local = 0, chunk_no = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
       const int buf = local & 1;
       const uint32_t aph = (uint32_t)(local >> 1) & 1u;
       const int m0 = (tile / n_tiles) * GM, n0 = (tile % n_tiles) * GN;
       ptx::mbar_wait(acc_full + buf, aph);
       ptx::tc_fence_after_sync();
-      const int row = m0 + q * 32 + lane;
-      float* crow = C + (int64_t)row * N;
 #pragma unroll 1
-      for (int c0 = 0; c0 < GN; c0 += 32) {
+      for (int c0 = 0; c0 < GN; c0 += 32, ++chunk_no) {
         uint32_t r[32];
         ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * G_ACC_COLS + c0, r);
         ptx::tmem_ld_wait();
-        if (row < M) {
+        if (c0 + 32 >= GN) {                              // last read of this accumulator: hand it back
+          ptx::tc_fence_before_sync();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(acc_empty + buf);
+        }
+        unsigned char* stg = out_stage + (chunk_no & 1) * G_OUT_BYTES;
+        // the store that used this staging buffer two chunks ago must have finished reading it
+        if (warp == 4 && lane == 0) ptx::bulk_wait_group_read<1>();
+        ptx::named_bar_sync(1, 128);
+        float4* row = reinterpret_cast<float4*>(stg + r_in_tile * 128);
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const int n = n0 + c0 + j;
-            if (n + 3 < N) {
-              float4 bv = bias ? __ldg(reinterpret_cast<const float4*>(bias + n)) : make_float4(0.f, 0.f, 0.f, 0.f);
-              float4 o;
-              o.x = __uint_as_float(r[j]) + bv.x;
-              o.y = __uint_as_float(r[j + 1]) + bv.y;
-              o.z = __uint_as_float(r[j + 2]) + bv.z;
-              o.w = __uint_as_float(r[j + 3]) + bv.w;
-              *reinterpret_cast<float4*>(crow + n) = o;
-            } else {
-              for (int e = 0; e < 4; ++e)
-                if (n + e < N) crow[n + e] = __uint_as_float(r[j + e]) + (bias ? bias[n + e] : 0.f);
-            }
-          }
+        for (int j = 0; j < 8; ++j) {
+          const int n = n0 + c0 + 4 * j;
+          float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (bias && n + 3 < N) bv = __ldg(reinterpret_cast<const float4*>(bias + n));
+          float4 o;
+          o.x = __uint_as_float(r[4 * j + 0]) + bv.x;
+          o.y = __uint_as_float(r[4 * j + 1]) + bv.y;
+          o.z = __uint_as_float(r[4 * j + 2]) + bv.z;
+          o.w = __uint_as_float(r[4 * j + 3]) + bv.w;
+          row[j ^ (r_in_tile & 7)] = o;                   // SWIZZLE_128B: 16-byte chunk index XOR (row mod 8)
+        }
+        ptx::fence_proxy_async_smem();
+        ptx::named_bar_sync(1, 128);
+        if (warp == 4 && lane == 0) {
+          ptx::tma_store_2d(&map_c, stg, n0 + c0, m0);
+          ptx::bulk_commit_group();
         }
       }
-      ptx::tc_fence_before_sync();
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(acc_empty + buf);
     }
+    if (warp == 4 && lane == 0) ptx::bulk_wait_group<0>();
   }
 
   ptx::tc_fence_before_sync();
@@ -172,8 +185,14 @@ static PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
   return fn;
 }
 
+int make_rowmajor_map(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, int box_rows, bool tf32);
+
 // row-major fp32 [rows, cols] matrix, box = [box_rows, 32 floats], SWIZZLE_128B, OOB -> 0
 int make_tf32_rowmajor_map(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, int box_rows) {
+  return make_rowmajor_map(map, base, rows, cols, box_rows, true);
+}
+
+int make_rowmajor_map(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, int box_rows, bool tf32) {
   auto enc = get_encode_fn();
   TTR_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled entry point not available");
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
@@ -182,7 +201,7 @@ int make_tf32_rowmajor_map(CUtensorMap* map, const float* base, int64_t rows, in
   cuuint32_t estr[2] = {1u, 1u};
   // TFLOAT32 lets the copy engine present tf32-typed data; bit 1 of the debug flags selects
   // plain FLOAT32 (hardware truncation in the MMA) for the rounding experiment in the tests.
-  CUtensorMapDataType dt = (g_debug_flags & 2) ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_TFLOAT32;
+  CUtensorMapDataType dt = (!tf32 || (g_debug_flags & 2)) ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_TFLOAT32;
   CUresult r = enc(map, dt, 2, const_cast<float*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -201,16 +220,18 @@ extern "C" int ttr_gemm_tf32_bias(const float* A, const float* W, const float* b
   TTR_REQUIRE(((uintptr_t)A & 15) == 0 && ((uintptr_t)W & 15) == 0 && ((uintptr_t)C & 15) == 0 &&
                   ((uintptr_t)bias & 15) == 0,
               "ttr_gemm_tf32_bias: operands must be 16-byte aligned");
-  CUtensorMap map_a, map_w;
+  CUtensorMap map_a, map_w, map_c;
   int rc = make_tf32_rowmajor_map(&map_a, A, m_bound, K, GM);
   if (rc != TTR_OK) return rc;
   rc = make_tf32_rowmajor_map(&map_w, W, N, K, GN);
   if (rc != TTR_OK) return rc;
-  const size_t smem = (size_t)G_STAGES * G_STAGE_BYTES + (2 * G_STAGES + 4) * sizeof(uint64_t) + 16 + 1024;
+  rc = make_rowmajor_map(&map_c, C, m_bound, N, GM, false);
+  if (rc != TTR_OK) return rc;
+  const size_t smem = (size_t)G_STAGES * G_STAGE_BYTES + 2 * G_OUT_BYTES + (2 * G_STAGES + 4) * sizeof(uint64_t) + 16 + 1024;
   TTR_CHECK_CUDA(cudaFuncSetAttribute(gemm_tf32_bias_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int tiles = ceil_div(m_bound, GM) * ceil_div(N, GN);
   const int grid = std::min(tiles, sm_count());
-  gemm_tf32_bias_kernel<<<grid, G_THREADS, smem, (cudaStream_t)stream>>>(map_a, map_w, bias, C, m_bound, m_valid, N, K);
+  gemm_tf32_bias_kernel<<<grid, G_THREADS, smem, (cudaStream_t)stream>>>(map_a, map_w, map_c, bias, m_bound, m_valid, N, K);
   TTR_CHECK_LAUNCH();
   return TTR_OK;
 }
