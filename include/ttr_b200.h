@@ -175,6 +175,15 @@ int ttr_score_topk(const float* Q, int B, const float* docs, int64_t N, int D, i
 int ttr_topk_merge(const float* cand_scores, const int64_t* cand_idx, int P, int B, int kin,
                    int k, float* out_scores, int64_t* out_idx, void* stream);
 
+/* Same merge, but the P candidate lists are read IN PLACE from peer GPUs (symmetric-memory
+ * buffers mapped over NVLink): peer_*_h are HOST arrays of P device addresses, each pointing to
+ * that rank's [B, kin] scores (fp32) / global ids (int64, -1 = empty) / optional TF-IDF payload
+ * (fp64, array may be NULL).  The exchange and the merge are one kernel (no all-gather); the
+ * caller provides the cross-rank barrier before the launch.  P <= 16. */
+int ttr_topk_merge_peers(const uint64_t* peer_scores_h, const uint64_t* peer_idx_h,
+                         const uint64_t* peer_tfidf_h, int P, int B, int kin, int k,
+                         float* out_scores, int64_t* out_idx, double* out_tfidf, void* stream);
+
 /* ---- K14: hybrid rerank ----------------------------------------------------------------
  * Replaces frontend/main.py:158-198: semantic = 2*cos-1 (space=0, Chroma default squared-L2)
  * or cos (space=1); tfidf = <doc TF-IDF row, query TF-IDF row> (L2-normalised CSR rows);

@@ -28,6 +28,7 @@ def _worker(rank, world, port, q):
         full_csr = CsrF64.from_arrays(indptr, indices, data, dev)
         lo, hi = shard_bounds(N, world, rank)
         idx = ShardedIndex(D[lo:hi].contiguous(), lo, N, tfidf_local=full_csr.row_slice(lo, hi))
+        idx_nccl = ShardedIndex(D[lo:hi].contiguous(), lo, N, tfidf_local=full_csr.row_slice(lo, hi), peer_memory=False)
         qptr = np.arange(0, 4 * 5 + 1, 4)
         rng = np.random.default_rng(1)
         qidx = np.concatenate([np.sort(rng.choice(F, 4, replace=False)) for _ in range(5)])
@@ -37,11 +38,19 @@ def _worker(rank, world, port, q):
             s, i = idx.search(Q, 50)
             s1, i1 = search_topk(Q, D, 50)
             out[f"search{B}"] = bool(torch.equal(i, i1) and torch.allclose(s, s1, atol=1e-6))
+            s2, i2 = idx_nccl.search(Q, 50)
+            out[f"search{B}"] &= bool(torch.equal(i2, i1) and torch.equal(s2, s))
+            for _ in range(3):                      # buffer alternation over repeated calls
+                s3, i3 = idx.search(Q, 50)
+            out[f"search{B}"] &= bool(torch.equal(i3, i1))
         Q = torch.tensor(synth.make_unit_rows(5, 256, seed=9), device=dev)
         h = idx.search_hybrid(Q, qcsr, alpha=0.4, k=50, top_n=10)
         s1, i1 = search_topk(Q, D, 50)
         h1 = hybrid_rerank(i1, s1, 0.4, docs_csr=full_csr, q_csr=qcsr, top_n=10)
         out["hybrid"] = bool(torch.equal(h["idx"], h1["idx"]) and torch.equal(h["final"], h1["final"]))
+        h2 = idx_nccl.search_hybrid(Q, qcsr, alpha=0.4, k=50, top_n=10)
+        out["hybrid"] &= bool(torch.equal(h2["idx"], h1["idx"]) and torch.equal(h2["final"], h1["final"]))
+        out["peer_memory"] = bool(idx.peer_memory)
         # ---- data-parallel training step: 2 ranks x 8 triplets == 1 rank x 16 triplets
         cfg = synth.default_config(vocab_size=3000, embed_dim=200)
         cfg["DROPOUT"] = 0.0
@@ -108,6 +117,7 @@ def test_two_rank_sharded_search_hybrid_and_dp_training():
     for rank in (0, 1):
         r = res[rank]
         assert r["search3"] and r["search40"] and r["hybrid"], r
+        assert r["peer_memory"], "symmetric-memory exchange was not active"
         # mean-of-means over equal shards == mean over the global batch; clip + Adam identical up to fp32
         # reduction order.  Two Adam steps at lr=1e-3 move every weight by ~1e-3 each; elements whose
         # gradient is ~eps may differ by a few percent of that.

@@ -299,6 +299,80 @@ topk_merge_kernel(const float* __restrict__ cand_s, const IdxT* __restrict__ can
   }
 }
 
+// Cross-rank merge over PEER MEMORY: every rank's [B, kin] candidate lists (scores, global ids,
+// optional TF-IDF payload) live in symmetric buffers mapped into this process; the kernel reads
+// them through NVLink directly — the exchange and the merge are one launch, no all-gather.
+// Ordering: (score desc, source position asc); shards are ascending row ranges and each list
+// is sorted by (score desc, id asc), so source order == id order among equal scores.
+constexpr int MAX_PEERS = 16;
+struct PeerLists {
+  const float* s[MAX_PEERS];
+  const int64_t* i[MAX_PEERS];
+  const double* t[MAX_PEERS];
+};
+
+__global__ void __launch_bounds__(SC_THREADS)
+topk_merge_peers_kernel(PeerLists pl, int P, int kin, int k, float* __restrict__ out_s, int64_t* __restrict__ out_i,
+                        double* __restrict__ out_t) {
+  __shared__ float buf_s[SC_WARPS][TOPK_CAP];
+  __shared__ int32_t buf_i[SC_WARPS][TOPK_CAP];
+  __shared__ int cnts[SC_WARPS];
+  __shared__ float mrg_s[SC_WARPS * TOPK_KMAX];
+  __shared__ int32_t mrg_i[SC_WARPS * TOPK_KMAX];
+  const int q = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float tau_s = -INFINITY;
+  int32_t tau_i = IDX_PAD;
+  int cnt = 0;
+  const int total = P * kin;
+  for (int t0 = warp * 32; t0 < total; t0 += SC_THREADS) {
+    const int t = t0 + lane;
+    float s = -INFINITY;
+    int32_t src = IDX_PAD;
+    if (t < total) {
+      const int p = t / kin, j = t % kin;
+      if (pl.i[p][(int64_t)q * kin + j] >= 0) {
+        s = pl.s[p][(int64_t)q * kin + j];
+        src = t;
+      }
+    }
+    const bool pass = src != IDX_PAD && key_better<int32_t>(s, src, tau_s, tau_i);
+    const unsigned m = __ballot_sync(0xffffffffu, pass);
+    if (m) {
+      if (pass) {
+        int pos = cnt + __popc(m & ((1u << lane) - 1));
+        buf_s[warp][pos] = s;
+        buf_i[warp][pos] = src;
+      }
+      cnt += __popc(m);
+      __syncwarp();
+      if (cnt > TOPK_CAP - 32) {
+        cnt = warp_compact<int32_t>(buf_s[warp], buf_i[warp], cnt, k, lane, tau_s, tau_i);
+        __syncwarp();
+      }
+    }
+  }
+  cnt = warp_compact<int32_t>(buf_s[warp], buf_i[warp], cnt, k, lane, tau_s, tau_i);
+  if (lane == 0) cnts[warp] = cnt;
+  __syncthreads();
+  for (int t = threadIdx.x; t < SC_WARPS * TOPK_KMAX; t += blockDim.x) {
+    int w = t / TOPK_KMAX, j = t % TOPK_KMAX;
+    bool valid = j < cnts[w];
+    mrg_s[t] = valid ? buf_s[w][j] : -INFINITY;
+    mrg_i[t] = valid ? buf_i[w][j] : IDX_PAD;
+  }
+  __syncthreads();
+  block_bitonic_desc<int32_t>(mrg_s, mrg_i, SC_WARPS * TOPK_KMAX);
+  for (int j = threadIdx.x; j < k; j += blockDim.x) {
+    const int src = mrg_i[j];
+    const bool valid = src != IDX_PAD;
+    const int p = valid ? src / kin : 0, e = valid ? src % kin : 0;
+    out_s[(int64_t)q * k + j] = mrg_s[j];
+    out_i[(int64_t)q * k + j] = valid ? pl.i[p][(int64_t)q * kin + e] : (int64_t)-1;
+    if (out_t) out_t[(int64_t)q * k + j] = (valid && pl.t[p]) ? pl.t[p][(int64_t)q * kin + e] : 0.0;
+  }
+}
+
 static int simt_grid_parts() { return sm_count(); }
 
 template <int QB>
@@ -375,6 +449,23 @@ extern "C" int ttr_topk_merge(const float* cand_scores, const int64_t* cand_idx,
   // candidate layout [P][B][kin]
   topk_merge_kernel<int64_t><<<B, SC_THREADS, 0, (cudaStream_t)stream>>>(
       cand_scores, cand_idx, P, B, kin, (int64_t)B * kin, (int64_t)kin, k, 0, out_scores, out_idx);
+  TTR_CHECK_LAUNCH();
+  return TTR_OK;
+}
+
+extern "C" int ttr_topk_merge_peers(const uint64_t* peer_scores_h, const uint64_t* peer_idx_h,
+                                    const uint64_t* peer_tfidf_h, int P, int B, int kin, int k, float* out_scores,
+                                    int64_t* out_idx, double* out_tfidf, void* stream) {
+  using namespace ttr;
+  TTR_REQUIRE(k >= 1 && k <= TOPK_KMAX, "ttr_topk_merge_peers: k=%d outside [1, %d]", k, TOPK_KMAX);
+  TTR_REQUIRE(P >= 1 && P <= MAX_PEERS && B >= 1 && kin >= 1, "ttr_topk_merge_peers: bad shape (P=%d)", P);
+  PeerLists pl;
+  for (int p = 0; p < MAX_PEERS; ++p) {
+    pl.s[p] = p < P ? reinterpret_cast<const float*>(peer_scores_h[p]) : nullptr;
+    pl.i[p] = p < P ? reinterpret_cast<const int64_t*>(peer_idx_h[p]) : nullptr;
+    pl.t[p] = (p < P && peer_tfidf_h) ? reinterpret_cast<const double*>(peer_tfidf_h[p]) : nullptr;
+  }
+  topk_merge_peers_kernel<<<B, SC_THREADS, 0, (cudaStream_t)stream>>>(pl, P, kin, k, out_scores, out_idx, out_tfidf);
   TTR_CHECK_LAUNCH();
   return TTR_OK;
 }

@@ -191,9 +191,11 @@ __global__ void seed_tau_kernel(float* tau, const float* __restrict__ sample_s, 
 }
 
 // Scratch layout per CTA c = slice * n_qt + qt (thread ql = query inside the tile):
-//   out_s  [c][slot][ql] fp32   final candidate scores        (slot < SM_KEEP)
-//   out_i  [c][slot][ql] i32    final candidate ids
-//   out_n  [c][ql] i32          final count
+// Scratch layout (q = global query index, padded to 128 per tile):
+//   out_s  [q][slice][slot] fp32   final candidate scores   (slot < SM_KEEP)
+//   out_i  [q][slice][slot] i32    final candidate ids
+//   out_n  [q][slice] i32          final count
+// (query-major so that the merge kernel reads each query's candidates as one contiguous run)
 __global__ void __launch_bounds__(SM_THREADS, 1)
 score_topk_mma_kernel(const float* __restrict__ Q, const __grid_constant__ CUtensorMap map_d, int B, int64_t N,
                       int k, int n_slices, float* __restrict__ tau_g, float* __restrict__ out_s,
@@ -414,15 +416,14 @@ score_topk_mma_kernel(const float* __restrict__ Q, const __grid_constant__ CUten
     // final: leave at most SM_KEEP candidates, publish scores + count (ids stay in the scratch)
     __syncwarp();
     if (__any_sync(0xffffffffu, cnt > SM_KEEP)) cnt = thread_compact(ls, li, cnt, k, tau, strict);
-    float* os = out_s + ((size_t)cta * SM_KEEP) * SM_MQ + ql;
-    int32_t* oi = out_i + ((size_t)cta * SM_KEEP) * SM_MQ + ql;
+    const size_t ob = ((size_t)(q0 + ql) * n_slices + slice) * SM_KEEP;
     for (int e = 0; e < SM_KEEP; ++e)
       if (e < cnt) {
         const int lid = li[e * SM_MQ];                       // local -> global: tile = slice + it * n_slices
-        os[e * SM_MQ] = ls[e * SM_MQ];
-        oi[e * SM_MQ] = (int32_t)(((int64_t)slice + (int64_t)(lid >> 5) * n_slices) * SM_ND + (lid & 31));
+        out_s[ob + e] = ls[e * SM_MQ];
+        out_i[ob + e] = (int32_t)(((int64_t)slice + (int64_t)(lid >> 5) * n_slices) * SM_ND + (lid & 31));
       }
-    out_n[cta * SM_MQ + ql] = q_valid ? cnt : 0;
+    out_n[(size_t)(q0 + ql) * n_slices + slice] = q_valid ? cnt : 0;
   }
 
   ptx::tc_fence_before_sync();
@@ -441,7 +442,6 @@ topk_merge_tiled_kernel(const float* __restrict__ out_s, const int32_t* __restri
   __shared__ float mrg_s[8 * TOPK_KMAX];
   __shared__ int32_t mrg_i[8 * TOPK_KMAX];
   const int q = blockIdx.x;
-  const int qt = q / SM_MQ, ql = q % SM_MQ;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float tau_s = -INFINITY;
   int32_t tau_i = IDX_PAD;
@@ -453,10 +453,9 @@ topk_merge_tiled_kernel(const float* __restrict__ out_s, const int32_t* __restri
     int32_t ix = IDX_PAD;
     if (t < total) {
       const int slice = t / SM_KEEP, e = t % SM_KEEP;
-      const int cta = slice * n_qt + qt;
-      if (e < out_n[cta * SM_MQ + ql]) {
-        s = out_s[((size_t)cta * SM_KEEP + e) * SM_MQ + ql];
-        ix = out_i[((size_t)cta * SM_KEEP + e) * SM_MQ + ql];
+      if (e < __ldg(out_n + (size_t)q * n_slices + slice)) {
+        s = out_s[(size_t)q * total + t];
+        ix = out_i[(size_t)q * total + t];
       }
     }
     const bool pass = ix != IDX_PAD && key_better<int32_t>(s, ix, tau_s, tau_i);
@@ -535,8 +534,9 @@ int launch_score_topk_mma(const float* Q, int B, const float* docs, int64_t N, i
   // tiles appending and compacting almost everything it sees (3-4 k cycles per tile instead
   // of ~1.2 k; profiles/r1_score_topk_mma_v4_trace_*).  The bound is valid for any document
   // order; its tightness only matters for speed.
-  const int64_t n_sample = (int64_t)sm_count() * 8 * SM_ND;
-  if (N >= 8 * n_sample && !(g_debug_flags & 256)) {
+  // 8 tiles per SM for big shards, 4 for small ones (the pass costs ~60-100 us of mostly fixed latency)
+  const int64_t n_sample = (int64_t)sm_count() * (N >= 4000000 ? 8 : 4) * SM_ND;
+  if (N >= 16 * n_sample && !(g_debug_flags & 256)) {
     MmaPlan ps = mma_plan(B, n_sample);
     CUtensorMap map_s;
     int rc = make_tf32_rowmajor_map(&map_s, docs, n_sample, SM_DIM, SM_ND);

@@ -157,6 +157,57 @@ def shard_bounds(n_rows: int, world: int, rank: int) -> Tuple[int, int]:
     return lo, min(n_rows, lo + per)
 
 
+class _PeerExchange:
+    """Symmetric-memory candidate buffers: every rank writes its local [B, k] top-k (scores, global
+    ids, optional TF-IDF payload) into its own buffer; after a device-side barrier the merge kernel
+    of every rank reads all R buffers in place over NVLink (ttr_topk_merge_peers) — no all-gather.
+    Two buffers alternate so a fast rank never overwrites what a slow peer is still reading."""
+
+    def __init__(self, group, device, max_b: int, k: int):
+        import ctypes
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+        self.ctypes = ctypes
+        self.k, self.max_b = k, max_b
+        self.world = dist.get_world_size(group)
+        n = max_b * k
+        self.off_s, self.off_i, self.off_t = 0, n * 4, n * 12
+        self.stride = (n * 20 + 255) // 256 * 256
+        self.buf = symm.empty(2 * self.stride, dtype=torch.uint8, device=device)
+        grp = group if group is not None else dist.group.WORLD
+        self.hdl = symm.rendezvous(self.buf, grp)
+        self.ptrs = [int(p) for p in self.hdl.buffer_ptrs]
+        self.step = 0
+
+    def views(self, B: int):
+        p = self.step & 1
+        base = p * self.stride
+        n = B * self.k
+        s = self.buf[base + self.off_s: base + self.off_s + n * 4].view(torch.float32).view(B, self.k)
+        i = self.buf[base + self.off_i: base + self.off_i + n * 8].view(torch.int64).view(B, self.k)
+        t = self.buf[base + self.off_t: base + self.off_t + n * 8].view(torch.float64).view(B, self.k)
+        return s, i, t
+
+    def merge(self, B: int, with_tfidf: bool):
+        """Barrier, then one kernel that reads every rank's lists over peer memory."""
+        ct = self.ctypes
+        p = self.step & 1
+        self.step += 1
+        self.hdl.barrier(channel=p)
+        base = p * self.stride
+        arr = ct.c_uint64 * self.world
+        ps = arr(*[a + base + self.off_s for a in self.ptrs])
+        pi = arr(*[a + base + self.off_i for a in self.ptrs])
+        pt = arr(*[a + base + self.off_t for a in self.ptrs]) if with_tfidf else None
+        dev = self.buf.device
+        out_s = torch.empty(B, self.k, dtype=torch.float32, device=dev)
+        out_i = torch.empty(B, self.k, dtype=torch.int64, device=dev)
+        out_t = torch.empty(B, self.k, dtype=torch.float64, device=dev) if with_tfidf else None
+        _lib.call("ttr_topk_merge_peers", ct.addressof(ps), ct.addressof(pi), ct.addressof(pt) if pt else None,
+                  self.world, B, self.k, self.k, out_s, out_i, out_t)
+        return out_s, out_i, out_t
+
+
 class ShardedIndex:
     """Row-sharded exact index: each rank keeps `docs_local` fp32 [n_local, 256] resident in HBM.
 
@@ -165,7 +216,7 @@ class ShardedIndex:
     the number of shards.  With `group=None` and world size 1 no collective is issued."""
 
     def __init__(self, docs_local: torch.Tensor, row_offset: int = 0, n_total: Optional[int] = None,
-                 group=None, tfidf_local: Optional[CsrF64] = None):
+                 group=None, tfidf_local: Optional[CsrF64] = None, peer_memory: bool = True):
         _lib.require_cuda(docs_local, "ShardedIndex(docs_local)")
         self.docs = docs_local.contiguous()
         self.row_offset = int(row_offset)
@@ -176,19 +227,48 @@ class ShardedIndex:
         self._dist = dist
         self.world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
         self.rank = dist.get_rank(group) if self.world > 1 else 0
+        self.peer_memory = bool(peer_memory) and self.world > 1
+        self._px: Optional[_PeerExchange] = None
 
-    def _local(self, Q, k):
+    def _exchange(self, B: int, k: int) -> Optional[_PeerExchange]:
+        """Symmetric-memory exchange state (created collectively on first use / growth)."""
+        if not self.peer_memory:
+            return None
+        if self._px is None or self._px.k != k or self._px.max_b < B:
+            try:
+                self._px = _PeerExchange(self.group, self.docs.device, max(B, 128), k)
+            except Exception as e:     # no P2P mapping on this box: keep the NCCL all-gather exchange
+                import warnings
+                warnings.warn(f"peer-memory exchange unavailable ({e!r}); using NCCL all-gather")
+                self.peer_memory = False
+                return None
+        return self._px
+
+    def _local(self, Q, k, out=None):
         if self.docs.shape[0] == 0:
             B = Q.shape[0]
-            return (torch.full((B, k), float("-inf"), device=Q.device),
-                    torch.full((B, k), -1, dtype=torch.int64, device=Q.device))
-        return search_topk(Q, self.docs, k, self.row_offset)
+            s = torch.full((B, k), float("-inf"), device=Q.device)
+            i = torch.full((B, k), -1, dtype=torch.int64, device=Q.device)
+            if out is not None:
+                out[0].copy_(s)
+                out[1].copy_(i)
+                return out
+            return s, i
+        return search_topk(Q, self.docs, k, self.row_offset, out=out)
 
     def search(self, Q: torch.Tensor, k: int = 50):
-        s, i = self._local(Q, k)
         if self.world == 1:
-            return s, i
-        B = s.shape[0]
+            return self._local(Q, k)
+        if Q.dim() == 1:
+            Q = Q.unsqueeze(0)
+        B = Q.shape[0]
+        px = self._exchange(B, k)
+        if px is not None:
+            vs, vi, _ = px.views(B)
+            self._local(Q, k, out=(vs, vi))
+            ms, mi, _ = px.merge(B, with_tfidf=False)
+            return ms, mi
+        s, i = self._local(Q, k)
         gs = torch.empty(self.world, B, k, dtype=s.dtype, device=s.device)
         gi = torch.empty(self.world, B, k, dtype=i.dtype, device=i.device)
         self._dist.all_gather_into_tensor(gs, s, group=self.group)
@@ -202,6 +282,18 @@ class ShardedIndex:
         all-gather, so no rank needs another rank's CSR slice."""
         if self.tfidf is None:
             raise ValueError("ShardedIndex was built without a TF-IDF shard")
+        if Q.dim() == 1:
+            Q = Q.unsqueeze(0)
+        px = self._exchange(Q.shape[0], k) if self.world > 1 else None
+        if px is not None:
+            B = Q.shape[0]
+            vs, vi, vt = px.views(B)
+            self._local(Q, k, out=(vs, vi))
+            vt.copy_(tfidf_candidates(vi, self.tfidf, q_csr))
+            s, i, tf = px.merge(B, with_tfidf=True)
+            out = hybrid_rerank(i, s, alpha, tfidf=tf, space=space, top_n=top_n)
+            out["dense_scores"], out["dense_idx"] = s, i
+            return out
         s, i = self._local(Q, k)
         tf = tfidf_candidates(i, self.tfidf, q_csr)
         if self.world > 1:
