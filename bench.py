@@ -104,6 +104,27 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def ncu_traffic(batch: int, shard_rows: int):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the scoring kernel from the committed
+    `ncu --set full` capture (profiles/r1_score_topk_mma_v4_ncu_raw.csv) — only valid for the exact
+    configuration that was captured (B=128, full corpus on one GPU); null otherwise."""
+    p = ROOT / "profiles" / "r1_score_topk_mma_v4_ncu_raw.csv"
+    if batch != 128 or shard_rows != N_DOCS or not p.exists():
+        return None
+    try:
+        import csv
+        rows = list(csv.reader(open(p)))
+        hdr, unit, last = rows[0], rows[1], rows[-1]
+        tot = 0.0
+        for name in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            i = hdr.index(name)
+            scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[unit[i]]
+            tot += float(last[i]) * scale
+        return tot
+    except Exception:
+        return None
+
+
 def make_shard(n_rows: int, seed: int, device) -> torch.Tensor:
     """F.normalize(N(0,1)) rows generated on the device in chunks (seed 3 + rank)."""
     out = torch.empty(n_rows, DIM, dtype=torch.float32, device=device)
@@ -268,9 +289,10 @@ def run_b200(args):
         "config": bench_config(args, world),
         "e2e": {"value": B / (ms_e2e * 1e-3), "unit": "queries/s", "h2d_bytes_per_step": B * DIM * 4,
                 "d2h_bytes_per_step": B * TOPK * 12, "ms_per_step": ms_e2e},
-        "gpu_launches": K * ((2 if B <= 4 else 6) + (1 if world > 1 else 0)),
+        # B <= 4: streaming kernel + merge; B > 4: init, [sample scan, merge, seed,] main scan, merge; + peer merge
+        "gpu_launches": K * ((2 if B <= 4 else (6 if shard_rows >= 16 * 148 * 4 * 32 else 3)) + (2 if world > 1 else 0)),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                     "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                     "frac": achieved / hbm_peak, "traffic": ncu_traffic(B, shard_rows), "peak_source": peak_src,
                      "kernel": ("score_topk_stream_kernel" if B <= 4 else "score_topk_mma_kernel") +
                                " (+ topk_merge_kernel, ~1% of the call)",
                      "algorithmic_bytes_per_call": algo_bytes, "ms_per_call": ms_kern,
@@ -297,7 +319,13 @@ def extras(index, dev, world, rank, timed, hbm_peak):
     rows = index.docs.shape[0]
     out["search_batch1"] = {"queries_per_s": 1e3 / ms, "ms": ms,
                             "hbm_gbs_per_gpu": rows * BYTES_PER_DOC / (ms * 1e-3) / 1e9,
-                            "hbm_frac": rows * BYTES_PER_DOC / (ms * 1e-3) / 1e9 / hbm_peak}
+                            "hbm_frac": rows * BYTES_PER_DOC / (ms * 1e-3) / 1e9 / hbm_peak,
+                            "note": "includes the cross-rank merge at N > 1"}
+    q4k = make_queries(4096, 1).to(dev)
+    ms = timed(lambda s: index.search(q4k[0], TOPK), 3)
+    flops = 2.0 * 4096 * N_DOCS * DIM
+    out["search_batch4096"] = {"queries_per_s": 4096e3 / ms, "ms": ms, "tf32_tflops_whole_job": flops / (ms * 1e-3) / 1e12,
+                               "note": "BASELINE configs[3] shape; tensor/epilogue-bound regime (kind::tf32)"}
     try:
         from twotowermlretrieval_b200 import TwoTowerModel, synth
         cfg = synth.default_config()

@@ -178,24 +178,27 @@ constexpr int SM_TRACE_TILES = 256;   // trace buffer: 8 roles x 256 tiles
       trace[(role) * SM_TRACE_TILES + _ti] = clock64();                                         \
   } while (0)
 
-__global__ void init_tau_kernel(float* tau, int n) {
+__global__ void init_tau_kernel(float* tau, int32_t* qcount, int n) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) tau[i] = -INFINITY;
+  if (i < n) { tau[i] = -INFINITY; qcount[i] = 0; }
 }
 
 // tau[q] = k-th best score of the sample pass (a valid lower bound on the final k-th best)
-__global__ void seed_tau_kernel(float* tau, const float* __restrict__ sample_s, const int64_t* __restrict__ sample_i,
-                                int B, int k) {
+__global__ void seed_tau_kernel(float* tau, int32_t* qcount, const float* __restrict__ sample_s,
+                                const int64_t* __restrict__ sample_i, int B, int n_pad, int k) {
   int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q < n_pad) qcount[q] = 0;
   if (q < B && sample_i[(int64_t)q * k + (k - 1)] >= 0) tau[q] = sample_s[(int64_t)q * k + (k - 1)];
 }
 
 // Scratch layout per CTA c = slice * n_qt + qt (thread ql = query inside the tile):
-// Scratch layout (q = global query index, padded to 128 per tile):
-//   out_s  [q][slice][slot] fp32   final candidate scores   (slot < SM_KEEP)
-//   out_i  [q][slice][slot] i32    final candidate ids
-//   out_n  [q][slice] i32          final count
-// (query-major so that the merge kernel reads each query's candidates as one contiguous run)
+// Scratch layout (q = global query index, padded to 128 per tile; cap = n_slices * SM_KEEP):
+//   out_s  [q][cap] fp32   candidate scores, appended by the CTAs in arrival order
+//   out_i  [q][cap] i32    candidate ids
+//   out_n  [q] i32         number of candidates (atomic cursor)
+// A CTA only publishes candidates >= the global bound tau_g it sees when it finishes (k documents
+// at or above that bound exist somewhere, so anything below cannot be in the top-k): a few
+// hundred entries per query reach the merge kernel instead of n_slices * 64.
 __global__ void __launch_bounds__(SM_THREADS, 1)
 score_topk_mma_kernel(const float* __restrict__ Q, const __grid_constant__ CUtensorMap map_d, int B, int64_t N,
                       int k, int n_slices, float* __restrict__ tau_g, float* __restrict__ out_s,
@@ -416,14 +419,19 @@ score_topk_mma_kernel(const float* __restrict__ Q, const __grid_constant__ CUten
     // final: leave at most SM_KEEP candidates, publish scores + count (ids stay in the scratch)
     __syncwarp();
     if (__any_sync(0xffffffffu, cnt > SM_KEEP)) cnt = thread_compact(ls, li, cnt, k, tau, strict);
-    const size_t ob = ((size_t)(q0 + ql) * n_slices + slice) * SM_KEEP;
-    for (int e = 0; e < SM_KEEP; ++e)
-      if (e < cnt) {
-        const int lid = li[e * SM_MQ];                       // local -> global: tile = slice + it * n_slices
-        out_s[ob + e] = ls[e * SM_MQ];
-        out_i[ob + e] = (int32_t)(((int64_t)slice + (int64_t)(lid >> 5) * n_slices) * SM_ND + (lid & 31));
-      }
-    out_n[(size_t)(q0 + ql) * n_slices + slice] = q_valid ? cnt : 0;
+    if (q_valid) {
+      const float tgf = __ldcg(tau_g + q);
+      int n_keep = 0;
+      for (int e = 0; e < SM_KEEP; ++e) n_keep += (e < cnt && ls[e * SM_MQ] >= tgf) ? 1 : 0;
+      size_t ob = (size_t)q * ((size_t)n_slices * SM_KEEP) + (size_t)atomicAdd(out_n + q, n_keep);
+      for (int e = 0; e < SM_KEEP; ++e)
+        if (e < cnt && ls[e * SM_MQ] >= tgf) {
+          const int lid = li[e * SM_MQ];                     // local -> global: tile = slice + it * n_slices
+          out_s[ob] = ls[e * SM_MQ];
+          out_i[ob] = (int32_t)(((int64_t)slice + (int64_t)(lid >> 5) * n_slices) * SM_ND + (lid & 31));
+          ++ob;
+        }
+    }
   }
 
   ptx::tc_fence_before_sync();
@@ -446,17 +454,15 @@ topk_merge_tiled_kernel(const float* __restrict__ out_s, const int32_t* __restri
   float tau_s = -INFINITY;
   int32_t tau_i = IDX_PAD;
   int cnt = 0;
-  const int total = n_slices * SM_KEEP;
+  const size_t cap = (size_t)n_slices * SM_KEEP;
+  const int total = out_n[q];
   for (int t0 = warp * 32; t0 < total; t0 += 256) {
     const int t = t0 + lane;
     float s = -INFINITY;
     int32_t ix = IDX_PAD;
     if (t < total) {
-      const int slice = t / SM_KEEP, e = t % SM_KEEP;
-      if (e < __ldg(out_n + (size_t)q * n_slices + slice)) {
-        s = out_s[(size_t)q * total + t];
-        ix = out_i[(size_t)q * total + t];
-      }
+      s = out_s[(size_t)q * cap + t];
+      ix = out_i[(size_t)q * cap + t];
     }
     const bool pass = ix != IDX_PAD && key_better<int32_t>(s, ix, tau_s, tau_i);
     const unsigned m = __ballot_sync(0xffffffffu, pass);
@@ -512,7 +518,7 @@ MmaPlan mma_plan(int B, int64_t N) {
   p.outs_off = align(bp * 4);
   p.outi_off = align(p.outs_off + (int64_t)p.n_ctas * SM_KEEP * SM_MQ * 4);
   p.outn_off = align(p.outi_off + (int64_t)p.n_ctas * SM_KEEP * SM_MQ * 4);
-  p.total = align(p.outn_off + (int64_t)p.n_ctas * SM_MQ * 4);
+  p.total = align(p.outn_off + bp * 4);
   return p;
 }
 
@@ -525,7 +531,7 @@ int launch_score_topk_mma(const float* Q, int B, const float* docs, int64_t N, i
   int32_t* outi = reinterpret_cast<int32_t*>(ws + p.outi_off);
   int32_t* outn = reinterpret_cast<int32_t*>(ws + p.outn_off);
   const int nq_pad = p.n_qt * SM_MQ;
-  init_tau_kernel<<<ceil_div(nq_pad, 256), 256, 0, st>>>(tau, nq_pad);
+  init_tau_kernel<<<ceil_div(nq_pad, 256), 256, 0, st>>>(tau, outn, nq_pad);
   TTR_CHECK_LAUNCH();
   const size_t smem = (size_t)SM_STAGES * SM_STAGE_BYTES + SM_LIST_BYTES + SM_LISTI_BYTES + (2 * SM_STAGES + 2 * SM_NACC) * 8 + 16 + 1024;
   TTR_CHECK_CUDA(cudaFuncSetAttribute(score_topk_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -547,7 +553,7 @@ int launch_score_topk_mma(const float* Q, int B, const float* docs, int64_t N, i
     TTR_CHECK_LAUNCH();
     topk_merge_tiled_kernel<<<B, 256, 0, st>>>(outs, outi, outn, ps.n_qt, ps.n_slices, k, 0, out_scores, out_idx);
     TTR_CHECK_LAUNCH();
-    seed_tau_kernel<<<ceil_div(B, 256), 256, 0, st>>>(tau, out_scores, out_idx, B, k);
+    seed_tau_kernel<<<ceil_div(nq_pad, 256), 256, 0, st>>>(tau, outn, out_scores, out_idx, B, nq_pad, k);
     TTR_CHECK_LAUNCH();
   }
   CUtensorMap map_d;
