@@ -71,6 +71,14 @@ int ttr_debug_gemm_fp32_bias(const float* A, const float* W, const float* bias, 
  * dW = dG^T X of the GRU backward (autograd of backend/main.py:254).  fp32 split-K. */
 int ttr_gemm_tn_fp32(const float* A, const float* Bm, float* C, int m_bound,
                      const int32_t* m_valid, int N, int K, int accumulate, void* stream);
+/* Tensor-core version of the same contraction on column blocks of wider matrices:
+ * C[N1, N2] (+)= A[0:m_valid, 0:N1]^T * Bm[0:m_valid, 0:N2], row pitches lda/ldb/ldc (multiples of 4).
+ * tcgen05 kind::tf32 with MN-major operands, split-K, TMA reduce-add epilogue.  The caller must zero
+ * rows [m_valid, round_up(m_valid, 32)) of both operands (ttr_zero_tail_rows). */
+int ttr_gemm_tn_tf32(const float* A, int lda, const float* Bm, int ldb, float* C, int ldc, int m_bound,
+                     const int32_t* m_valid, int N1, int N2, int accumulate, void* stream);
+/* rows [m_valid, min(m_bound, round_up(m_valid, 32))) of a row-major [m_bound, ld] matrix := 0 */
+int ttr_zero_tail_rows(float* A, int m_bound, const int32_t* m_valid, int ld, void* stream);
 /* C[M, K] = A[M, N] * W[N, K]  (dX = dG W_ih), tcgen05 tf32 is not needed for parity of
  * gradients; fp32 CUDA cores. */
 int ttr_gemm_nn_fp32(const float* A, const float* W, float* C, int m_bound,
@@ -99,7 +107,8 @@ int ttr_gru_recurrence_bwd(const float* dy, const float* dh_last, const float* y
                            void* stream);
 /* dW_hh[dir] (+)= dgh[:, dir]^T h_prev[:, dir], where h_prev is y shifted by one step inside
  * each row (0 at a row's first step).  hprev_ws: scratch fp32 [m_bound, dirs*H].
- * Out: dw_hh [dirs, 3H, H].  (Bias gradients are column sums: ttr_colsum.) */
+ * Out: dw_hh [dirs, 3H, H].  (Bias gradients are column sums: ttr_colsum.)  Runs ttr_gemm_tn_tf32:
+ * the caller zeroes the tail rows of dgh first; H and 3H must be multiples of 4. */
 int ttr_gru_whh_grad(const float* dgh, const float* y, const int32_t* offsets, int B, int H,
                      int dirs, int m_bound, float* hprev_ws, float* dw_hh, int accumulate,
                      void* stream);

@@ -66,3 +66,28 @@ def test_tf32_operand_rounding_probe(cuda_device):
         print(f"\n[tf32 probe] {name}: hw(1 + i*2^-14) in units of 2^-14, i=0..47: {steps[:48]}")
         assert all(abs(v - i) <= 16 for i, v in enumerate(steps))          # within one tf32 ulp (2^-10)
     print("[tf32 probe] identical across map types:", res["TFLOAT32 map"] == res["FLOAT32 map"])
+
+
+@pytest.mark.parametrize("M,N1,N2,lda_extra,ldb_extra", [(64, 128, 128, 0, 0), (1000, 1536, 200, 0, 0), (5000, 768, 256, 768, 256),
+                                                          (333, 96, 12, 0, 0), (40000, 1536, 512, 0, 0), (31, 48, 20, 48, 0)])
+def test_tn_weight_gradient_gemm_matches_fp64(cuda_device, M, N1, N2, lda_extra, ldb_extra):
+    """C = A[:M]^T B[:M] (MN-major tcgen05 + split-K + TMA reduce-add) vs fp64, incl. column blocks of wider
+    matrices, a dynamic row count and accumulate."""
+    g = torch.Generator(device=cuda_device).manual_seed(M + N1 + N2)
+    m_bound = M + 77
+    A = torch.randn(m_bound, N1 + lda_extra, device=cuda_device, generator=g) * 0.1
+    Bm = torch.randn(m_bound, N2 + ldb_extra, device=cuda_device, generator=g)
+    A[M:] = float("nan")                      # rows beyond m_valid are garbage until the tail is zeroed
+    Bm[M:] = float("nan")
+    mv = torch.tensor([M], dtype=torch.int32, device=cuda_device)
+    for t in (A, Bm):
+        _lib.call("ttr_zero_tail_rows", t, m_bound, mv, t.shape[1])
+    a_view, b_view = A[:, lda_extra:], Bm[:, ldb_extra:]     # column blocks with pitch > width
+    C = torch.full((N1, N2), float("nan"), device=cuda_device)
+    _lib.call("ttr_gemm_tn_tf32", a_view, A.shape[1], b_view, Bm.shape[1], C, N2, m_bound, mv, N1, N2, 0)
+    ref = a_view[:M].double().t() @ b_view[:M].double()
+    scale = float((a_view[:M].double().abs().t() @ b_view[:M].double().abs()).max())
+    err = float((C.double() - ref).abs().max())
+    assert err <= 1.5e-3 * scale, (err, scale)
+    _lib.call("ttr_gemm_tn_tf32", a_view, A.shape[1], b_view, Bm.shape[1], C, N2, m_bound, mv, N1, N2, 1)
+    assert float((C.double() - 2 * ref).abs().max()) <= 3e-3 * scale

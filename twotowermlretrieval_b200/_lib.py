@@ -28,6 +28,8 @@ _SIGNATURES = {
     "ttr_debug_gemm_fp32_bias": [P, P, P, P, I32, P, I32, I32, P],
     "ttr_gemm_tn_fp32": [P, P, P, I32, P, I32, I32, I32, P],
     "ttr_gemm_nn_fp32": [P, P, P, I32, P, I32, I32, I32, P],
+    "ttr_gemm_tn_tf32": [P, I32, P, I32, P, I32, I32, P, I32, I32, I32, P],
+    "ttr_zero_tail_rows": [P, I32, P, I32, P],
     "ttr_gru_recurrence_fwd": [P, P, P, P, P, I32, I32, I32, P, P, P, P],
     "ttr_gru_recurrence_bwd": [P, P, P, P, P, P, P, I32, I32, I32, P, P, P],
     "ttr_gru_whh_grad": [P, P, P, I32, I32, I32, I32, P, P, I32, P],

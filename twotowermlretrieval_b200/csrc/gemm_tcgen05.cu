@@ -186,6 +186,8 @@ static PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
 }
 
 int make_rowmajor_map(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, int box_rows, bool tf32);
+int make_pitched_map(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, int64_t pitch, int box_rows,
+                     bool tf32, bool atom32 = false);
 
 // row-major fp32 [rows, cols] matrix, box = [box_rows, 32 floats], SWIZZLE_128B, OOB -> 0
 int make_tf32_rowmajor_map(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, int box_rows) {
@@ -193,17 +195,23 @@ int make_tf32_rowmajor_map(CUtensorMap* map, const float* base, int64_t rows, in
 }
 
 int make_rowmajor_map(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, int box_rows, bool tf32) {
+  return make_pitched_map(map, base, rows, cols, cols, box_rows, tf32);
+}
+
+// [rows, cols] view of a row-major matrix with row pitch `pitch` floats (a column block of a wider matrix)
+int make_pitched_map(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, int64_t pitch, int box_rows,
+                     bool tf32, bool atom32) {
   auto enc = get_encode_fn();
   TTR_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled entry point not available");
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)cols * 4};
+  cuuint64_t strides[1] = {(cuuint64_t)pitch * 4};
   cuuint32_t box[2] = {32u, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1u, 1u};
   // TFLOAT32 lets the copy engine present tf32-typed data; bit 1 of the debug flags selects
   // plain FLOAT32 (hardware truncation in the MMA) for the rounding experiment in the tests.
   CUtensorMapDataType dt = (!tf32 || (g_debug_flags & 2)) ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_TFLOAT32;
   CUresult r = enc(map, dt, 2, const_cast<float*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   TTR_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with CUresult %d (rows=%lld cols=%lld)", (int)r,
               (long long)rows, (long long)cols);

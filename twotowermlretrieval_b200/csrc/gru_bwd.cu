@@ -287,10 +287,6 @@ gru_hprev_kernel(const float* __restrict__ y, const int32_t* __restrict__ offset
   }
 }
 
-int launch_gemm_strided(const float* A, int64_t sa_i, int64_t sa_l, const float* Bm, int64_t sb_l, int64_t sb_j,
-                        float* C, int64_t ldc, int I, int J, int L, const int32_t* dyn, int dyn_which,
-                        int accumulate, int allow_split, cudaStream_t st);
-
 }  // namespace ttr
 
 extern "C" int ttr_gru_recurrence_bwd(const float* dy, const float* dh_last, const float* y, const float* saved,
@@ -327,10 +323,12 @@ extern "C" int ttr_gru_whh_grad(const float* dgh, const float* y, const int32_t*
   gru_hprev_kernel<<<B, 128, 0, st>>>(y, offsets, H, dirs, hprev_ws);
   TTR_CHECK_LAUNCH();
   const int G3 = 3 * H;
+  int rc = ttr_zero_tail_rows(hprev_ws, m_bound, offsets + B, dirs * H, stream);
+  if (rc != TTR_OK) return rc;
   for (int dir = 0; dir < dirs; ++dir) {
-    // dW_hh[dir] [3H, H] (+)= dgh[:, dir*3H : (dir+1)*3H]^T * hprev[:, dir*H : (dir+1)*H]
-    int rc = launch_gemm_strided(dgh + dir * G3, 1, (int64_t)dirs * G3, hprev_ws + dir * H, (int64_t)dirs * H, 1,
-                                 dw_hh + (size_t)dir * G3 * H, H, G3, H, m_bound, offsets + B, 2, accumulate, 1, st);
+    // dW_hh[dir] [3H, H] (+)= dgh[:, dir*3H : (dir+1)*3H]^T * hprev[:, dir*H : (dir+1)*H]   (tcgen05, split-K)
+    rc = ttr_gemm_tn_tf32(dgh + dir * G3, dirs * G3, hprev_ws + dir * H, dirs * H, dw_hh + (size_t)dir * G3 * H, H,
+                          m_bound, offsets + B, G3, H, accumulate, stream);
     if (rc != TTR_OK) return rc;
   }
   return TTR_OK;

@@ -70,18 +70,24 @@ def encoder_backward(enc, ctx: dict, d_out: torch.Tensor) -> List[Optional[torch
         dgh = torch.empty(Mb, G, dtype=torch.float32, device=dev)
         _lib.call("ttr_gru_recurrence_bwd", dy, dh_last, ctx["ys"][layer], ctx["saveds"][layer], W_hh,
                   plan.order, plan.offsets, B, H, dirs, dgi, dgh)
+        # weight gradients on the tensor cores (tf32, token dimension reduced with split-K); the
+        # operands' rows between the valid token count and the next multiple of 32 must be zero
+        layer_in = ctx["layer_ins"][layer]
+        for t, ld in ((dgi, G), (dgh, G), (layer_in, in_dim)):
+            _lib.call("ttr_zero_tail_rows", t, Mb, plan.total, ld)
         hprev = torch.empty(Mb, dirs * H, dtype=torch.float32, device=dev)
         _lib.call("ttr_gru_whh_grad", dgh, ctx["ys"][layer], plan.offsets, B, H, dirs, Mb, hprev,
                   gview("weight_hh", layer), 0)
         del hprev
         _lib.call("ttr_colsum", dgh, Mb, plan.total, G, gview("bias_hh", layer), 0)
         _lib.call("ttr_colsum", dgi, Mb, plan.total, G, gview("bias_ih", layer), 0)
-        _lib.call("ttr_gemm_tn_fp32", dgi, ctx["layer_ins"][layer], gview("weight_ih", layer), Mb, plan.total,
+        _lib.call("ttr_gemm_tn_tf32", dgi, G, layer_in, in_dim, gview("weight_ih", layer), in_dim, Mb, plan.total,
                   G, in_dim, 0)
         del dgh
         if layer > 0:
+            # dX = dG W_ih through the tcgen05 NT kernel: B operand = W_ih^T [in, G] (3 MB transpose)
             dx = torch.empty(Mb, in_dim, dtype=torch.float32, device=dev)
-            _lib.call("ttr_gemm_nn_fp32", dgi, W_ih, dx, Mb, plan.total, G, in_dim, 0)
+            _lib.call("ttr_gemm_tf32_bias", dgi, W_ih.t().contiguous(), None, dx, Mb, plan.total, in_dim, G)
             mask = ctx["masks"][layer - 1]
             if mask is not None:
                 dx.mul_(mask)
