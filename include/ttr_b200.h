@@ -216,6 +216,26 @@ int ttr_tfidf_candidates(const int64_t* cand_idx, int B, int kc, int64_t csr_row
                          const double* data, const int64_t* q_indptr, const int32_t* q_indices,
                          const double* q_data, double* out, void* stream);
 
+/* Inter-layer dropout of nn.GRU in train mode (backend/model.py:35, DROPOUT in backend/config.json):
+ * mask[i] = (u_i >= p) / (1 - p) with u_i from a counter-based generator of (seed, i);
+ * out = y * mask.  The mask is kept for the backward pass and can be exported for oracle replay. */
+int ttr_dropout(const float* y, int64_t n, float p, uint64_t seed, float* out, float* mask, void* stream);
+
+/* ---- corpus-wide hybrid search ----------------------------------------------------------
+ * Replaces `SimpleHybridRetriever.search` (backend/simple_hybrid.py:45-66) for ONE query:
+ * combined[i] = float32(alpha * cos(q, docs[i])) + (1 - alpha) * <tfidf row i, query tfidf row>
+ * over all N documents (sklearn cosine_similarity semantics: both sides normalised, zero rows
+ * give 0), then the top k in `np.argsort(combined)[::-1]` order (ties: HIGHER index first).
+ * q fp32 [D] (device), q_norm = ||q||; docs fp32 [N, D]; doc CSR as in ttr_hybrid_rerank; the
+ * query's TF-IDF row as (q_idx int32 sorted, q_val fp64, q_nnz).  out_scores fp64 [k], out_idx
+ * int64 [k]; combined_out optional fp64 [N]; workspace ttr_blend_topk_workspace_bytes(k) bytes. */
+int64_t ttr_blend_topk_workspace_bytes(int k);
+int ttr_blend_topk(const float* q, float q_norm, const float* docs, int64_t N, int D,
+                   const int64_t* indptr, const int32_t* indices, const double* data,
+                   const int32_t* q_idx, const double* q_val, int q_nnz, double alpha, int k,
+                   double* out_scores, int64_t* out_idx, double* combined_out, void* workspace,
+                   void* stream);
+
 #ifdef __cplusplus
 }
 #endif

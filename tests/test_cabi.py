@@ -68,7 +68,8 @@ def test_binding_arity_and_types_match_header():
     text = (ROOT / "include" / "ttr_b200.h").read_text()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
     protos = dict(re.findall(r"\b(ttr_[a-z0-9_]+)\s*\(([^)]*)\)\s*;", text))
-    kinds = {ctypes.c_void_p: "p", ctypes.c_int: "i", ctypes.c_int64: "l", ctypes.c_float: "f", ctypes.c_double: "d"}
+    kinds = {ctypes.c_void_p: "p", ctypes.c_int: "i", ctypes.c_int64: "l", ctypes.c_uint64: "u", ctypes.c_float: "f",
+             ctypes.c_double: "d"}
     for name, sig in _lib._SIGNATURES.items():
         params = [p.strip() for p in protos[name].split(",") if p.strip() and p.strip() != "void"]
         want = []
@@ -77,6 +78,8 @@ def test_binding_arity_and_types_match_header():
                 want.append("p")
             elif p.startswith("int64_t"):
                 want.append("l")
+            elif p.startswith("uint64_t"):
+                want.append("u")
             elif p.startswith("int"):
                 want.append("i")
             elif p.startswith("float"):

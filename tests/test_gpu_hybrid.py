@@ -109,3 +109,42 @@ def test_inferencer_and_simple_hybrid_match_reference_run(cuda_device, tmp_path)
         assert got_idx == want or np.abs(np.diff(g["res_score"][qi])).min() < 1e-3
     batch = inf.encode_queries([q for qi, q in enumerate(queries) if not g["raises"][qi]] + [""])
     assert batch.shape[0] == 5 and not batch[-1].any()
+
+
+def test_corpus_wide_blend_kernel_vs_numpy(cuda_device):
+    """ttr_blend_topk == alpha*cos + (1-alpha)*tfidf over all docs, np.argsort()[::-1][:k] (simple_hybrid.py:57-60)."""
+    import scipy.sparse as sp
+    from twotowermlretrieval_b200 import _lib
+    rng = np.random.default_rng(11)
+    N, F, D = 20011, 500, 256
+    docs = (rng.standard_normal((N, D)) * 0.3).astype(np.float32)           # not unit norm on purpose
+    docs[17] = 0.0                                                          # zero row -> cosine 0
+    indptr, indices, data = synth.make_tfidf_csr(N, n_features=F, mean_nnz=10, seed=4)
+    M = sp.csr_matrix((data, indices, indptr), shape=(N, F))
+    csr = CsrF64.from_arrays(indptr, indices, data, cuda_device)
+    d_dev = torch.tensor(docs, device=cuda_device)
+    lib = _lib.load()
+    for alpha, k, qn in ((0.6, 10, 4), (0.0, 25, 3), (1.0, 64, 0)):
+        q = rng.standard_normal(D).astype(np.float32)
+        qi = np.sort(rng.choice(F, size=qn, replace=False)).astype(np.int32)
+        qv = rng.random(qn) + 0.1
+        qv = qv / np.linalg.norm(qv) if qn else qv
+        qd = np.zeros(F); qd[qi] = qv
+        dn = np.linalg.norm(docs, axis=1)
+        dense = np.where(dn > 0, (docs @ q) / np.maximum(dn * np.linalg.norm(q), 1e-30), 0.0).astype(np.float32)
+        comb = alpha * dense + (1 - alpha) * (M @ qd)
+        top, sc = onp.hybrid_search_simple(dense, M @ qd, alpha, k)
+        ws = torch.empty(int(lib.ttr_blend_topk_workspace_bytes(k)), dtype=torch.uint8, device=cuda_device)
+        out_s = torch.empty(k, dtype=torch.float64, device=cuda_device)
+        out_i = torch.empty(k, dtype=torch.int64, device=cuda_device)
+        full = torch.empty(N, dtype=torch.float64, device=cuda_device)
+        _lib.call("ttr_blend_topk", torch.tensor(q, device=cuda_device), float(np.linalg.norm(q)), d_dev, N, D,
+                  csr.indptr, csr.indices, csr.data, torch.tensor(qi, device=cuda_device),
+                  torch.tensor(qv, device=cuda_device), qn, alpha, k, out_s, out_i, full, ws)
+        np.testing.assert_allclose(full.cpu().numpy(), comb, rtol=0, atol=2e-6)
+        np.testing.assert_allclose(out_s.cpu().numpy(), sc, rtol=0, atol=2e-6)
+        got = out_i.cpu().numpy()
+        # exact agreement with the kernel's own combined vector, argsort()[::-1] tie order included
+        own = full.cpu().numpy()
+        assert (got == np.argsort(own, kind="stable")[::-1][:k]).all()
+        assert (got == top).mean() > 0.9

@@ -43,11 +43,14 @@ _SIGNATURES = {
     "ttr_score_topk": [P, I32, P, I64, I32, I32, I64, P, P, P, I64, P],
     "ttr_topk_merge": [P, P, I32, I32, I32, I32, P, P, P],
     "ttr_topk_merge_peers": [P, P, P, I32, I32, I32, I32, P, P, P, P],
+    "ttr_dropout": [P, I64, F32, ctypes.c_uint64, P, P, P],
+    "ttr_blend_topk": [P, F32, P, I64, I32, P, P, P, P, P, I32, F64, I32, P, P, P, P, P],
     "ttr_hybrid_rerank": [P, P, I32, I32, I64, P, P, P, P, P, P, P, F64, I32, I32, P, P, P, P, P],
     "ttr_tfidf_candidates": [P, I32, I32, I64, I64, P, P, P, P, P, P, P, P],
 }
 
-EXPORTED_SYMBOLS = sorted(list(_SIGNATURES) + ["ttr_last_error", "ttr_version", "ttr_score_topk_workspace_bytes"])
+EXPORTED_SYMBOLS = sorted(list(_SIGNATURES) + ["ttr_last_error", "ttr_version", "ttr_score_topk_workspace_bytes",
+                                               "ttr_blend_topk_workspace_bytes"])
 
 _lib = None
 
@@ -71,6 +74,8 @@ def load() -> ctypes.CDLL:
     lib.ttr_version.restype = ctypes.c_int
     lib.ttr_score_topk_workspace_bytes.restype = ctypes.c_int64
     lib.ttr_score_topk_workspace_bytes.argtypes = [I32, I64, I32]
+    lib.ttr_blend_topk_workspace_bytes.restype = ctypes.c_int64
+    lib.ttr_blend_topk_workspace_bytes.argtypes = [I32]
     for name, args in _SIGNATURES.items():
         fn = getattr(lib, name)
         fn.restype = ctypes.c_int

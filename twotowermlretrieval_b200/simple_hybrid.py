@@ -2,9 +2,10 @@
 
 `fit` keeps the reference's choices (documents go through the QUERY tower, quirk #10;
 `TfidfVectorizer(stop_words='english', max_features=10000)`), but encodes all documents in
-length-bucketed batches instead of one forward per document.  `search` blends
-alpha*dense_cos + (1-alpha)*tfidf_cos over the whole corpus and returns the `top_k` best
-`(document, score)` pairs in `np.argsort(...)[::-1]` order, like `simple_hybrid.py:57-66`.
+length-bucketed batches instead of one forward per document, and keeps the embeddings and the
+TF-IDF CSR resident on the device.  `search` runs one fused kernel pass over the corpus
+(`ttr_blend_topk`): alpha*dense_cos + (1-alpha)*tfidf_cos for every document and the `top_k`
+best `(document, score)` pairs in `np.argsort(...)[::-1]` order, like `simple_hybrid.py:57-66`.
 The text vectoriser stays host-side sklearn (string processing is out of scope).
 """
 from __future__ import annotations
@@ -14,6 +15,8 @@ from typing import List, Tuple
 import numpy as np
 import torch
 
+from . import _lib
+from .index import CsrF64
 from .query_inferencer import QueryInferencer
 
 
@@ -26,24 +29,35 @@ class SimpleHybridRetriever:
         self.documents: List[str] = []
         self.doc_embeddings = None          # np.float32 [N, H], like the reference attribute
         self._doc_dev = None                # resident copy, fp32 [N, H]
-        self._doc_norm = None
+        self._csr = None                    # resident TF-IDF matrix
+        self._ws = None
 
     def fit(self, documents: List[str]):
         self.documents = list(documents)
         self.tfidf_matrix = self.tfidf.fit_transform(self.documents)
-        self._doc_dev = self.dense_retriever.encode_queries(self.documents)     # query tower, quirk #10
+        dev = self.dense_retriever.device
+        self._doc_dev = self.dense_retriever.encode_queries(self.documents).contiguous()   # query tower, quirk #10
         self.doc_embeddings = self._doc_dev.cpu().numpy()
-        self._doc_norm = torch.linalg.vector_norm(self._doc_dev, dim=1)
+        self._csr = CsrF64.from_scipy(self.tfidf_matrix, dev)
 
     def search(self, query: str, top_k: int = 10) -> List[Tuple[str, float]]:
         dev = self._doc_dev.device
-        q_tfidf = self.tfidf.transform([query])
-        tfidf_scores = np.asarray((self.tfidf_matrix @ q_tfidf.T).todense()).ravel()   # L2 rows: cosine == dot
-        q = torch.from_numpy(self.dense_retriever.get_query_embedding(query)).to(dev)
-        # sklearn cosine_similarity (simple_hybrid.py:53-54): normalise both sides (zero rows stay zero)
-        qn = torch.linalg.vector_norm(q)
-        dense = (self._doc_dev @ q) / (self._doc_norm * qn).clamp_min(torch.finfo(torch.float32).tiny)
-        dense = torch.where((self._doc_norm == 0) | (qn == 0), torch.zeros_like(dense), dense)
-        combined = self.alpha * dense.double().cpu().numpy() + (1 - self.alpha) * tfidf_scores
-        top = np.argsort(combined)[::-1][:top_k]
-        return [(self.documents[i], combined[i]) for i in top]
+        N, D = self._doc_dev.shape
+        k = min(top_k, N)
+        q_row = self.tfidf.transform([query]).tocsr()
+        q_row.sort_indices()
+        q_idx = torch.as_tensor(q_row.indices.astype(np.int32), device=dev)
+        q_val = torch.as_tensor(q_row.data.astype(np.float64), device=dev)
+        q_np = self.dense_retriever.get_query_embedding(query)
+        q = torch.from_numpy(q_np).to(dev)
+        lib = _lib.load()
+        nbytes = lib.ttr_blend_topk_workspace_bytes(k)
+        if self._ws is None or self._ws.numel() < nbytes:
+            self._ws = torch.empty(int(nbytes), dtype=torch.uint8, device=dev)
+        out_s = torch.empty(k, dtype=torch.float64, device=dev)
+        out_i = torch.empty(k, dtype=torch.int64, device=dev)
+        _lib.call("ttr_blend_topk", q, float(np.linalg.norm(q_np)), self._doc_dev, N, D, self._csr.indptr,
+                  self._csr.indices, self._csr.data, q_idx, q_val, int(q_idx.numel()), float(self.alpha), k,
+                  out_s, out_i, None, self._ws)
+        idx, sc = out_i.cpu().tolist(), out_s.cpu().tolist()
+        return [(self.documents[i], s) for i, s in zip(idx, sc) if i >= 0]

@@ -110,8 +110,11 @@ def _forward_impl(enc, ids: torch.Tensor, need_grad: bool, training: bool):
             layer_in = y
             if p_drop > 0.0:
                 # inter-layer dropout of nn.GRU (model.py:35): scaled keep mask on layer outputs
-                mask = (torch.rand_like(y) >= p_drop).to(torch.float32).mul_(1.0 / (1.0 - p_drop))
-                layer_in = y * mask
+                # (seed drawn from torch's CPU generator so torch.manual_seed controls it)
+                seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+                mask = torch.empty_like(y)
+                layer_in = torch.empty_like(y)
+                _lib.call("ttr_dropout", y, y.numel(), float(p_drop), seed, layer_in, mask)
         masks.append(mask)
     out = torch.empty(B, H, dtype=torch.float32, device=dev)
     raw = torch.empty(B, H, dtype=torch.float32, device=dev) if need_grad else None
