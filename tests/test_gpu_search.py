@@ -92,6 +92,23 @@ def test_tcgen05_and_streaming_paths_agree(cuda_device):
     assert (i_mma == i_st).float().mean() > 0.9
 
 
+def test_select_merge_unstaged_path(cuda_device):
+    """The select-merge stages candidate keys in shared memory; sets too large for that are re-read
+    from L2 each radix round (debug flag bit 9 forces that path).  Same exact result either way."""
+    from twotowermlretrieval_b200 import _lib
+    D = torch.tensor(synth.make_unit_rows(60000, 256, seed=43), device=cuda_device)
+    D[20000:20300] = D[100:400]                                   # exact score ties across document slices
+    Q = torch.tensor(synth.make_unit_rows(130, 256, seed=44), device=cuda_device)
+    s_a, i_a = search_topk(Q, D, 50)
+    _lib.call_nostream("ttr_debug_set_flags", 512)
+    try:
+        s_b, i_b = search_topk(Q, D, 50)
+    finally:
+        _lib.call_nostream("ttr_debug_set_flags", 0)
+    assert torch.equal(s_a, s_b) and torch.equal(i_a, i_b)
+    check_topk(s_a[:8], i_a[:8], Q[:8].cpu().numpy(), D.cpu().numpy(), 50)
+
+
 def test_tcgen05_adversarial(cuda_device):
     rng = np.random.default_rng(1)
     Q = synth.make_unit_rows(16, 256, seed=5)

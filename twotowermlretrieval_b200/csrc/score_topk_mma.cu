@@ -54,6 +54,7 @@ constexpr int SM_KEEP = 64;                             // a compaction leaves k
 constexpr int SM_LIST_BYTES = SM_CAP * SM_MQ * 4;       // score lists ([slot][thread]): 64 KB
 constexpr int SM_LISTI_BYTES = SM_CAP * SM_MQ * 2;      // id lists, uint16 CTA-local document numbers: 32 KB
 constexpr int SM_MAX_TILES_PER_CTA = 65536 / SM_ND;     // so that a local document number fits 16 bits
+constexpr int SM_SAMPLE_TOP = 8;                        // candidates a CTA publishes per query in the sample pass
 
 __device__ __forceinline__ void atomic_max_float(float* addr, float v) {
   if (v >= 0.f) atomicMax(reinterpret_cast<int*>(addr), __float_as_int(v));
@@ -199,6 +200,14 @@ __global__ void seed_tau_kernel(float* tau, int32_t* qcount, const float* __rest
 // A CTA only publishes candidates >= the global bound tau_g it sees when it finishes (k documents
 // at or above that bound exist somewhere, so anything below cannot be in the top-k): a few
 // hundred entries per query reach the merge kernel instead of n_slices * 64.
+//
+// SAMPLE = true is the threshold-seeding pass over the first few tiles of every slice: the epilogue
+// thread keeps only its SM_SAMPLE_TOP best scores in registers (branch-free insertion, no lists,
+// no compaction) and publishes those.  The k-th best of the union over all CTAs is a valid lower
+// bound on the final k-th best (every published candidate is a real document), and it equals the
+// exact k-th best of the sample unless one CTA holds more than SM_SAMPLE_TOP of the sample's top k
+// (256 documents of ~38 k per CTA: mean 0.34 of the top 50).
+template <bool SAMPLE>
 __global__ void __launch_bounds__(SM_THREADS, 1)
 score_topk_mma_kernel(const float* __restrict__ Q, const __grid_constant__ CUtensorMap map_d, int B, int64_t N,
                       int k, int n_slices, float* __restrict__ tau_g, float* __restrict__ out_s,
@@ -244,18 +253,26 @@ score_topk_mma_kernel(const float* __restrict__ Q, const __grid_constant__ CUten
     const int qw = warp - 4;
     const int q = q0 + qw * 32 + lane;
     const float4* src = reinterpret_cast<const float4*>(Q + (int64_t)(q < B ? q : 0) * SM_DIM);
+    // two round trips of 32 independent 16-byte loads each (the row is 1 KB; eight dependent
+    // round trips of 8 loads cost ~8 us of the ~30 us fixed cost of a launch)
 #pragma unroll 1
-    for (int c0 = 0; c0 < SM_DIM; c0 += 32) {
-      uint32_t r[32];
+    for (int c0 = 0; c0 < SM_DIM; c0 += 128) {
+      float4 x[32];
 #pragma unroll
-      for (int v = 0; v < 8; ++v) {
-        float4 x = (q < B) ? __ldg(src + (c0 >> 2) + v) : make_float4(0.f, 0.f, 0.f, 0.f);
-        r[4 * v + 0] = __float_as_uint(round_tf32(x.x));
-        r[4 * v + 1] = __float_as_uint(round_tf32(x.y));
-        r[4 * v + 2] = __float_as_uint(round_tf32(x.z));
-        r[4 * v + 3] = __float_as_uint(round_tf32(x.w));
+      for (int v = 0; v < 32; ++v)
+        x[v] = (q < B) ? __ldg(src + (c0 >> 2) + v) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        uint32_t r[32];
+#pragma unroll
+        for (int v = 0; v < 8; ++v) {
+          r[4 * v + 0] = __float_as_uint(round_tf32(x[8 * g + v].x));
+          r[4 * v + 1] = __float_as_uint(round_tf32(x[8 * g + v].y));
+          r[4 * v + 2] = __float_as_uint(round_tf32(x[8 * g + v].z));
+          r[4 * v + 3] = __float_as_uint(round_tf32(x[8 * g + v].w));
+        }
+        ptx::tmem_st_32x32(tmem_base + ((uint32_t)(qw * 32) << 16) + c0 + 32 * g, r);
       }
-      ptx::tmem_st_32x32(tmem_base + ((uint32_t)(qw * 32) << 16) + c0, r);
     }
     ptx::tmem_st_wait();
   }
@@ -332,6 +349,10 @@ score_topk_mma_kernel(const float* __restrict__ Q, const __grid_constant__ CUten
     const bool q_valid = q < B;
     float* ls = list_s + ql;
     uint16_t* li = list_i + ql;   // CTA-local document number: it * 32 + j
+    float top_s[SM_SAMPLE_TOP];   // SAMPLE: best scores so far, descending
+    int32_t top_i[SM_SAMPLE_TOP];
+#pragma unroll
+    for (int e = 0; e < SM_SAMPLE_TOP; ++e) { top_s[e] = -INFINITY; top_i[e] = -1; }
     float tau = -INFINITY;                     // own bound on the k-th best
     bool strict = false;
     int cnt = 0;
@@ -377,7 +398,8 @@ score_topk_mma_kernel(const float* __restrict__ Q, const __grid_constant__ CUten
       if (qw == 0) SM_TRACE(4, it);
       const int64_t d0 = t * SM_ND;
       // one threshold, one compare per score: "strictly above tau" == ">= next float above tau"
-      const float thr = fmaxf(tg, strict ? key2f(f2key(tau) + 1u) : tau);
+      const float thr = SAMPLE ? key2f(f2key(top_s[SM_SAMPLE_TOP - 1]) + 1u)      // must beat the weakest kept score
+                               : fmaxf(tg, strict ? key2f(f2key(tau) + 1u) : tau);
       // Branch-free filter -> per-lane bit mask of surviving documents.  (A short-circuit
       // condition compiles to a branch per score: ~45 cycles of resolve latency each with one
       // warp per scheduler, 1300-1600 cycles per tile; profiles/r1_score_topk_mma_v4_trace_*.)
@@ -402,20 +424,45 @@ score_topk_mma_kernel(const float* __restrict__ Q, const __grid_constant__ CUten
           SM_CASE(24) SM_CASE(25) SM_CASE(26) SM_CASE(27) SM_CASE(28) SM_CASE(29) SM_CASE(30) SM_CASE(31)
 #undef SM_CASE
         }
-        if ((mask >> j) & 1u) {   // cnt <= SM_CAP - SM_ND before the tile, so 32 free slots exist
+        if (SAMPLE) {
+          // bubble the candidate through the sorted registers; lanes whose score did not pass carry -inf
+          float cs = ((mask >> j) & 1u) ? scj : -INFINITY;
+          int32_t ci = (int32_t)(d0 + j);
+#pragma unroll
+          for (int e = 0; e < SM_SAMPLE_TOP; ++e) {
+            const bool up = cs > top_s[e];
+            const float ts = top_s[e];
+            const int32_t ti = top_i[e];
+            top_s[e] = up ? cs : ts;
+            top_i[e] = up ? ci : ti;
+            cs = up ? ts : cs;
+            ci = up ? ti : ci;
+          }
+        } else if ((mask >> j) & 1u) {   // cnt <= SM_CAP - SM_ND before the tile, so 32 free slots exist
           ls[cnt * SM_MQ] = scj;
           li[cnt * SM_MQ] = (uint16_t)(it * SM_ND + j);
           ++cnt;
         }
       }
       if (qw == 0) SM_TRACE(6, it);
-      if (__any_sync(0xffffffffu, cnt > SM_CAP - SM_ND)) {
+      if (!SAMPLE && __any_sync(0xffffffffu, cnt > SM_CAP - SM_ND)) {
         __syncwarp();
         cnt = thread_compact(ls, li, cnt, k, tau, strict);
         if (q_valid && cnt >= k) atomic_max_float(tau_g + q, tau);
       }
       if (qw == 0) SM_TRACE(7, it);
     }
+    if (SAMPLE) {
+      if (q_valid) {
+        int n_keep = 0;
+#pragma unroll
+        for (int e = 0; e < SM_SAMPLE_TOP; ++e) n_keep += top_i[e] >= 0 ? 1 : 0;
+        size_t ob = (size_t)q * ((size_t)n_slices * SM_KEEP) + (size_t)atomicAdd(out_n + q, n_keep);
+#pragma unroll
+        for (int e = 0; e < SM_SAMPLE_TOP; ++e)
+          if (top_i[e] >= 0) { out_s[ob] = top_s[e]; out_i[ob] = top_i[e]; ++ob; }
+      }
+    } else {
     // final: leave at most SM_KEEP candidates, publish scores + count (ids stay in the scratch)
     __syncwarp();
     if (__any_sync(0xffffffffu, cnt > SM_KEEP)) cnt = thread_compact(ls, li, cnt, k, tau, strict);
@@ -432,6 +479,7 @@ score_topk_mma_kernel(const float* __restrict__ Q, const __grid_constant__ CUten
           ++ob;
         }
     }
+    }
   }
 
   ptx::tc_fence_before_sync();
@@ -439,63 +487,191 @@ score_topk_mma_kernel(const float* __restrict__ Q, const __grid_constant__ CUten
   if (warp == 2) ptx::tmem_dealloc(tmem_base, SM_TMEM_COLS);
 }
 
-// One CTA per query: gather the <= SM_KEEP candidates of every document slice, exact top-k.
-__global__ void __launch_bounds__(256)
-topk_merge_tiled_kernel(const float* __restrict__ out_s, const int32_t* __restrict__ out_i,
-                        const int32_t* __restrict__ out_n, int n_qt, int n_slices, int k, int64_t idx_offset,
-                        float* __restrict__ res_s, int64_t* __restrict__ res_i) {
-  __shared__ float buf_s[8][TOPK_CAP];
-  __shared__ int32_t buf_i[8][TOPK_CAP];
-  __shared__ int cnts[8];
-  __shared__ float mrg_s[8 * TOPK_KMAX];
-  __shared__ int32_t mrg_i[8 * TOPK_KMAX];
-  const int q = blockIdx.x;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float tau_s = -INFINITY;
-  int32_t tau_i = IDX_PAD;
-  int cnt = 0;
-  const size_t cap = (size_t)n_slices * SM_KEEP;
-  const int total = out_n[q];
-  for (int t0 = warp * 32; t0 < total; t0 += 256) {
-    const int t = t0 + lane;
-    float s = -INFINITY;
-    int32_t ix = IDX_PAD;
-    if (t < total) {
-      s = out_s[(size_t)q * cap + t];
-      ix = out_i[(size_t)q * cap + t];
+// ---------------------------------------------------------------------------------------------
+// Select-merge: one CTA per query picks the exact top-k of the candidates the scoring CTAs
+// published (~n_slices * 50..64 of them: 9 k per query at 148 slices) and sorts those k.
+//
+// Every candidate becomes one 64-bit key, (order-preserving score bits << 32) | ~index, so
+// "better" (higher score, then lower index — the total order of every other top-k stage) is a
+// plain unsigned compare and all keys are distinct.  The keys are staged in shared memory with
+// many independent loads in flight, the k-th largest key is found by a most-significant-digit
+// radix select (8-bit digits, shared-memory histograms, starting below the bits all keys share),
+// exactly k keys are collected and a 64-slot bitonic network orders them.
+// The previous merge streamed the candidates through warp buffers with a dependent global load
+// per 256 candidates: ~65 us per call whatever the count (profiles/r1_search_b128_launch_list.md).
+constexpr int MG_THREADS = 512;
+constexpr int MG_MAX_STAGE = 20480;        // keys staged in shared memory (160 KB); larger sets are re-read from L2
+
+__device__ __forceinline__ uint64_t cand_key(float s, int32_t ix) {
+  return ((uint64_t)f2key(s + 0.0f) << 32) | (uint64_t)(0xffffffffu - (uint32_t)ix);   // -0 -> +0
+}
+
+template <bool STAGED>
+__device__ __forceinline__ uint64_t mg_key(const uint64_t* keys, const float* cs, const int32_t* ci, int t) {
+  if (STAGED) return keys[t];
+  return cand_key(__ldcg(cs + t), __ldcg(ci + t));
+}
+
+template <bool STAGED>
+__device__ __forceinline__ void select_merge_body(uint64_t* keys, const float* cs, const int32_t* ci, int total,
+                                                  int k, int64_t idx_offset, float* res_s, int64_t* res_i) {
+  __shared__ uint32_t hist[256];
+  __shared__ uint64_t red_and[MG_THREADS / 32], red_or[MG_THREADS / 32];
+  __shared__ uint64_t sel[TOPK_KMAX];
+  __shared__ uint64_t s_prefix;
+  __shared__ int s_remaining, s_done, s_nout, s_shift;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  uint64_t thresh = 0;                       // keys >= thresh are the answer
+  if (total > k) {
+    // bits shared by all keys need no histogram pass: AND/OR reduction finds them
+    uint64_t a = ~0ull, o = 0ull;
+    for (int t = tid; t < total; t += MG_THREADS) {
+      const uint64_t key = mg_key<STAGED>(keys, cs, ci, t);
+      a &= key; o |= key;
     }
-    const bool pass = ix != IDX_PAD && key_better<int32_t>(s, ix, tau_s, tau_i);
-    const unsigned m = __ballot_sync(0xffffffffu, pass);
-    if (m) {
-      if (pass) {
-        int pos = cnt + __popc(m & ((1u << lane) - 1));
-        buf_s[warp][pos] = s;
-        buf_i[warp][pos] = ix;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+      a &= __shfl_xor_sync(0xffffffffu, a, d);
+      o |= __shfl_xor_sync(0xffffffffu, o, d);
+    }
+    if (lane == 0) { red_and[warp] = a; red_or[warp] = o; }
+    __syncthreads();
+    if (tid == 0) {
+      for (int w = 1; w < MG_THREADS / 32; ++w) { a &= red_and[w]; o |= red_or[w]; }
+      const uint64_t diff = a ^ o;           // non-zero: the keys are distinct and total > k >= 1
+      const int top = 63 - __clzll((long long)diff);          // highest differing bit
+      const int shift = (top >> 3) << 3;                      // first digit = the byte holding that bit
+      s_shift = shift;
+      s_prefix = shift + 8 >= 64 ? 0ull : (a >> (shift + 8)) << (shift + 8);
+      s_remaining = k;
+      s_done = 0;
+    }
+    __syncthreads();
+    int shift = s_shift;
+    while (true) {
+      const uint64_t prefix = s_prefix;
+      const uint64_t hi_mask = shift + 8 >= 64 ? 0ull : (~0ull << (shift + 8));
+      for (int b = tid; b < 256; b += MG_THREADS) hist[b] = 0;
+      __syncthreads();
+      for (int t = tid; t < total; t += MG_THREADS) {
+        const uint64_t key = mg_key<STAGED>(keys, cs, ci, t);
+        if ((key & hi_mask) == (prefix & hi_mask)) atomicAdd(&hist[(uint32_t)(key >> shift) & 255u], 1u);
       }
-      cnt += __popc(m);
-      __syncwarp();
-      if (cnt > TOPK_CAP - 32) {
-        cnt = warp_compact<int32_t>(buf_s[warp], buf_i[warp], cnt, k, lane, tau_s, tau_i);
+      __syncthreads();
+      if (warp == 0) {
+        // lane l owns bins [8l, 8l+8); suffix sums over lanes find the bin holding the remaining-th key from the top
+        uint32_t h[8];
+        uint32_t own = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { h[j] = hist[8 * lane + j]; own += h[j]; }
+        uint32_t suf = own;                  // inclusive suffix sum over lanes >= lane
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          const uint32_t v = __shfl_down_sync(0xffffffffu, suf, d);
+          if (lane + d < 32) suf += v;
+        }
+        const uint32_t above = suf - own;    // keys in bins of higher lanes
+        const uint32_t rem = (uint32_t)s_remaining;
+        __syncwarp();                        // every lane has read s_remaining before one lane rewrites it
+        if (above < rem && rem <= suf) {
+          uint32_t cum = above;
+#pragma unroll
+          for (int j = 7; j >= 0; --j) {
+            if (cum < rem && rem <= cum + h[j]) {
+              s_prefix = (prefix & hi_mask) | ((uint64_t)(8 * lane + j) << shift);
+              s_remaining = (int)(rem - cum);
+              s_done = (h[j] == rem - cum) || shift == 0;      // the whole bin is taken: no need to look inside
+            }
+            cum += h[j];
+          }
+        }
+      }
+      __syncthreads();
+      if (s_done) break;
+      shift = shift >= 8 ? shift - 8 : 0;
+    }
+    thresh = s_prefix;                       // low bits zero: every key of the selected bin (and above) qualifies
+  }
+  if (tid == 0) s_nout = 0;
+  for (int j = tid; j < TOPK_KMAX; j += MG_THREADS) sel[j] = 0ull;
+  __syncthreads();
+  for (int t = tid; t < total; t += MG_THREADS) {
+    const uint64_t key = mg_key<STAGED>(keys, cs, ci, t);
+    if (key >= thresh) {
+      const int pos = atomicAdd(&s_nout, 1);
+      if (pos < TOPK_KMAX) sel[pos] = key;
+    }
+  }
+  __syncthreads();
+  if (warp == 0) {
+    // 64-slot bitonic network, descending; empty slots hold key 0 (below every real key)
+    for (int kk = 2; kk <= TOPK_KMAX; kk <<= 1) {
+      for (int j = kk >> 1; j > 0; j >>= 1) {
+        const int i = ((lane & ~(j - 1)) << 1) | (lane & (j - 1));
+        const int p = i | j;
+        const bool desc = (i & kk) == 0;
+        const uint64_t ki = sel[i], kp = sel[p];
+        if ((kp > ki) == desc) { sel[i] = kp; sel[p] = ki; }
         __syncwarp();
       }
     }
+    for (int j = lane; j < k; j += 32) {
+      const uint64_t key = sel[j];
+      const bool valid = key != 0ull;
+      res_s[j] = valid ? key2f((uint32_t)(key >> 32)) : -INFINITY;
+      res_i[j] = valid ? (int64_t)(0xffffffffu - (uint32_t)key) + idx_offset : (int64_t)-1;
+    }
   }
-  cnt = warp_compact<int32_t>(buf_s[warp], buf_i[warp], cnt, k, lane, tau_s, tau_i);
-  if (lane == 0) cnts[warp] = cnt;
-  __syncthreads();
-  for (int t = threadIdx.x; t < 8 * TOPK_KMAX; t += blockDim.x) {
-    int w = t / TOPK_KMAX, j = t % TOPK_KMAX;
-    bool valid = j < cnts[w];
-    mrg_s[t] = valid ? buf_s[w][j] : -INFINITY;
-    mrg_i[t] = valid ? buf_i[w][j] : IDX_PAD;
+}
+
+__global__ void __launch_bounds__(MG_THREADS)
+topk_select_merge_kernel(const float* __restrict__ out_s, const int32_t* __restrict__ out_i,
+                         const int32_t* __restrict__ out_n, int n_slices, int k, int64_t idx_offset, int stage_cap,
+                         float* __restrict__ res_s, int64_t* __restrict__ res_i) {
+  extern __shared__ uint64_t mg_keys[];
+  const int q = blockIdx.x;
+  const size_t cap = (size_t)n_slices * SM_KEEP;
+  const int total = out_n[q];
+  const float* cs = out_s + (size_t)q * cap;
+  const int32_t* ci = out_i + (size_t)q * cap;
+  float* rs = res_s + (int64_t)q * k;
+  int64_t* ri = res_i + (int64_t)q * k;
+  if (total <= stage_cap) {
+    // stage: four independent load pairs in flight per thread
+    int t = threadIdx.x;
+    for (; t + 3 * MG_THREADS < total; t += 4 * MG_THREADS) {
+      float s[4];
+      int32_t ix[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { s[u] = __ldcg(cs + t + u * MG_THREADS); ix[u] = __ldcg(ci + t + u * MG_THREADS); }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) mg_keys[t + u * MG_THREADS] = cand_key(s[u], ix[u]);
+    }
+    for (; t < total; t += MG_THREADS) mg_keys[t] = cand_key(__ldcg(cs + t), __ldcg(ci + t));
+    __syncthreads();
+    select_merge_body<true>(mg_keys, cs, ci, total, k, idx_offset, rs, ri);
+  } else {
+    select_merge_body<false>(mg_keys, cs, ci, total, k, idx_offset, rs, ri);
   }
-  __syncthreads();
-  block_bitonic_desc<int32_t>(mrg_s, mrg_i, 8 * TOPK_KMAX);
-  for (int j = threadIdx.x; j < k; j += blockDim.x) {
-    const bool valid = mrg_i[j] != IDX_PAD;
-    res_s[(int64_t)q * k + j] = mrg_s[j];
-    res_i[(int64_t)q * k + j] = valid ? (int64_t)mrg_i[j] + idx_offset : (int64_t)-1;
-  }
+}
+
+// stage capacity (keys) for a given slice count; bytes = 8 * capacity
+static int merge_stage_cap(int n_slices) {
+  const int64_t cap = (int64_t)n_slices * SM_KEEP;
+  return (int)std::min<int64_t>(cap, MG_MAX_STAGE);
+}
+
+static int launch_select_merge(const float* outs, const int32_t* outi, const int32_t* outn, int B, int n_slices, int k,
+                               int64_t idx_offset, float* res_s, int64_t* res_i, cudaStream_t st) {
+  const int stage_cap = (g_debug_flags & 512) ? 0 : merge_stage_cap(n_slices);   // bit 9: force the L2 re-read path
+  const size_t smem = (size_t)stage_cap * 8;
+  TTR_CHECK_CUDA(cudaFuncSetAttribute(topk_select_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      MG_MAX_STAGE * 8));
+  topk_select_merge_kernel<<<B, MG_THREADS, smem, st>>>(outs, outi, outn, n_slices, k, idx_offset, stage_cap, res_s,
+                                                       res_i);
+  TTR_CHECK_LAUNCH();
+  return TTR_OK;
 }
 
 struct MmaPlan {
@@ -534,25 +710,30 @@ int launch_score_topk_mma(const float* Q, int B, const float* docs, int64_t N, i
   init_tau_kernel<<<ceil_div(nq_pad, 256), 256, 0, st>>>(tau, outn, nq_pad);
   TTR_CHECK_LAUNCH();
   const size_t smem = (size_t)SM_STAGES * SM_STAGE_BYTES + SM_LIST_BYTES + SM_LISTI_BYTES + (2 * SM_STAGES + 2 * SM_NACC) * 8 + 16 + 1024;
-  TTR_CHECK_CUDA(cudaFuncSetAttribute(score_topk_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  TTR_CHECK_CUDA(cudaFuncSetAttribute(score_topk_mma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  TTR_CHECK_CUDA(cudaFuncSetAttribute(score_topk_mma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   // Sample pass: exact top-k of the first ~38 k documents gives every query a k-th-best bound
   // (top ~0.1 %) before the full scan starts.  Without it each CTA spends its first ~250
   // tiles appending and compacting almost everything it sees (3-4 k cycles per tile instead
   // of ~1.2 k; profiles/r1_score_topk_mma_v4_trace_*).  The bound is valid for any document
   // order; its tightness only matters for speed.
-  // 8 tiles per SM for big shards, 4 for small ones (the pass costs ~60-100 us of mostly fixed latency)
-  const int64_t n_sample = (int64_t)sm_count() * (N >= 4000000 ? 8 : 4) * SM_ND;
+  // 16 tiles per SM for big shards, 8 for small ones: since the sample epilogue keeps a register top-8
+  // instead of lists the pass is ~35 us fixed + ~4 us per tile, and a tighter bound saves the main
+  // pass more than that (measured: 8.8 M docs 8 -> 16 tiles 1.62 -> 1.56 ms; 1.1 M docs 4 -> 8 tiles
+  // 0.295 -> 0.275 ms per 128-query step)
+  const int tiles_override = (g_debug_flags >> 12) & 63;          // bits 12-17: sample tiles per SM (experiments)
+  const int64_t n_sample = (int64_t)sm_count() * (tiles_override ? tiles_override : (N >= 4000000 ? 16 : 8)) * SM_ND;
   if (N >= 16 * n_sample && !(g_debug_flags & 256)) {
     MmaPlan ps = mma_plan(B, n_sample);
     CUtensorMap map_s;
     int rc = make_tf32_rowmajor_map(&map_s, docs, n_sample, SM_DIM, SM_ND);
     if (rc != TTR_OK) return rc;
     dim3 gs(ps.n_qt, ps.n_slices);
-    score_topk_mma_kernel<<<gs, SM_THREADS, smem, st>>>(Q, map_s, B, n_sample, k, ps.n_slices, tau, outs, outi, outn,
-                                                       nullptr, g_debug_flags);
+    score_topk_mma_kernel<true><<<gs, SM_THREADS, smem, st>>>(Q, map_s, B, n_sample, k, ps.n_slices, tau, outs, outi,
+                                                             outn, nullptr, g_debug_flags);
     TTR_CHECK_LAUNCH();
-    topk_merge_tiled_kernel<<<B, 256, 0, st>>>(outs, outi, outn, ps.n_qt, ps.n_slices, k, 0, out_scores, out_idx);
-    TTR_CHECK_LAUNCH();
+    rc = launch_select_merge(outs, outi, outn, B, ps.n_slices, k, 0, out_scores, out_idx, st);
+    if (rc != TTR_OK) return rc;
     seed_tau_kernel<<<ceil_div(nq_pad, 256), 256, 0, st>>>(tau, outn, out_scores, out_idx, B, nq_pad, k);
     TTR_CHECK_LAUNCH();
   }
@@ -560,13 +741,10 @@ int launch_score_topk_mma(const float* Q, int B, const float* docs, int64_t N, i
   int rc = make_tf32_rowmajor_map(&map_d, docs, N, SM_DIM, SM_ND);
   if (rc != TTR_OK) return rc;
   dim3 grid(p.n_qt, p.n_slices);
-  score_topk_mma_kernel<<<grid, SM_THREADS, smem, st>>>(Q, map_d, B, N, k, p.n_slices, tau, outs, outi, outn,
-                                                        g_score_trace, g_debug_flags);
+  score_topk_mma_kernel<false><<<grid, SM_THREADS, smem, st>>>(Q, map_d, B, N, k, p.n_slices, tau, outs, outi, outn,
+                                                               g_score_trace, g_debug_flags);
   TTR_CHECK_LAUNCH();
-  topk_merge_tiled_kernel<<<B, 256, 0, st>>>(outs, outi, outn, p.n_qt, p.n_slices, k, row_offset, out_scores,
-                                            out_idx);
-  TTR_CHECK_LAUNCH();
-  return TTR_OK;
+  return launch_select_merge(outs, outi, outn, B, p.n_slices, k, row_offset, out_scores, out_idx, st);
 }
 
 int64_t score_topk_mma_workspace_bytes(int B, int64_t N) { return mma_plan(B, N).total; }
