@@ -123,7 +123,8 @@ int ttr_colsum(const float* A, int m_bound, const int32_t* m_valid, int N, float
 /* Test/debug switches: bit0 = force the generic (any-H) GRU kernels, bit1 = encode TMA maps
  * as FLOAT32 instead of TFLOAT32 (hardware truncation instead of round-to-nearest),
  * bit2 = force the CUDA-core streaming scorer for every batch size, bit8 = no sample pass,
- * bit9 = select-merge re-reads candidates from L2 instead of staging them in shared memory. */
+ * bit9 = select-merge re-reads candidates from L2 instead of staging them in shared memory,
+ * bit10 = H=256 GRU forward on the fp32 CUDA-core cluster kernel instead of the tcgen05 one. */
 int ttr_debug_set_flags(int flags);
 /* Diagnostic: device buffer (8 * 256 int64) receiving the pipeline timeline (SM clock at five
  * events per document tile) of CTA (0,0) of the tcgen05 scorer; NULL switches it off. */

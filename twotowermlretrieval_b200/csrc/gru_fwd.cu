@@ -264,6 +264,9 @@ gru_fwd_generic_kernel(GruFwdArgs a, int H) {
   }
 }
 
+int launch_gru_fwd_tc(const float* gi, const float* w_hh, const float* b_hh, const int32_t* order,
+                      const int32_t* offsets, int B, int dirs, float* y, float* h_last, float* saved, cudaStream_t st);
+
 }  // namespace ttr
 
 extern "C" int ttr_debug_set_flags(int flags) {
@@ -279,7 +282,11 @@ extern "C" int ttr_gru_recurrence_fwd(const float* gi, const float* w_hh, const 
   TTR_REQUIRE(h_last != nullptr, "ttr_gru_recurrence_fwd: h_last is required");
   cudaStream_t st = (cudaStream_t)stream;
   GruFwdArgs a{gi, w_hh, b_hh, order, offsets, B, dirs, y, h_last, saved};
-  if (H == GH && !(g_debug_flags & 1)) {
+  if (H == GH && !(g_debug_flags & (1 | 1024))) {
+    // default for H = 256: recurrent product on the tensor cores (gru_fwd_tc.cu)
+    return launch_gru_fwd_tc(gi, w_hh, b_hh, order, offsets, B, dirs, y, h_last, saved, st);
+  } else if (H == GH && !(g_debug_flags & 1)) {
+    // bit 10: the fp32 CUDA-core cluster kernel (W_hh in registers, warp-shuffle reductions)
     const size_t smem = (size_t)2 * GCL * GCS * sizeof(float) + 3 * GBT * sizeof(int);
     TTR_CHECK_CUDA(cudaFuncSetAttribute(gru_fwd_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(ceil_div(B, GBT) * GCL, dirs);
