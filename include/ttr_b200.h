@@ -93,10 +93,20 @@ int ttr_gemm_nn_fp32(const float* A, const float* W, float* C, int m_bound,
  * y       fp32 [Mtok, dirs*H]   per-step outputs (NULL if not needed)
  * h_last  fp32 [B, dirs*H]      final states in ORIGINAL row order
  * saved   fp32 [Mtok, dirs, 4, H] (r, z, n, W_hn h + b_hn) for the backward pass, or NULL
- * H == 256 runs the register-resident 8-CTA-cluster kernel; other H use a generic kernel. */
+ * H == 256 runs the register-resident 8-CTA-cluster kernel (fp32 CUDA cores, warp-shuffle
+ * reductions); other H use a generic kernel. */
 int ttr_gru_recurrence_fwd(const float* gi, const float* w_hh, const float* b_hh,
                            const int32_t* order, const int32_t* offsets, int B, int H, int dirs,
                            float* y, float* h_last, float* saved, void* stream);
+/* Same contract with a caller-owned scratch buffer of ttr_gru_fwd_workspace_bytes(B, H, dirs)
+ * bytes (uninitialised is fine; 0 for H != 256): H == 256 then runs the tcgen05 recurrence —
+ * W_hh slice resident in shared memory as fp16, h exchanged between the 8 CTAs of a cluster by
+ * multicast bulk copies through the (L2-resident) scratch, fp32 state and accumulation. */
+int64_t ttr_gru_fwd_workspace_bytes(int B, int H, int dirs);
+int ttr_gru_recurrence_fwd_ws(const float* gi, const float* w_hh, const float* b_hh,
+                              const int32_t* order, const int32_t* offsets, int B, int H, int dirs,
+                              float* y, float* h_last, float* saved, void* workspace,
+                              int64_t workspace_bytes, void* stream);
 /* BPTT of one layer.  In: dy [Mtok, dirs*H] (grad wrt per-step outputs, NULL = zero),
  * dh_last [B, dirs*H] (grad wrt final states, original row order, NULL = zero), y (this
  * layer's forward outputs), saved.  Out: dgi [Mtok, dirs*3H] (grad wrt gi, also the b_ih

@@ -60,12 +60,15 @@ def test_cfgdims_fp32_debug_gemm_and_generic_gru_agree(cuda_device, monkeypatch)
     x = torch.tensor(g["p"], device=cuda_device)
     monkeypatch.setenv("TTR_DEBUG_FP32_GEMM", "1")
     with torch.no_grad():
-        assert_rows_close(m.encode_document(x), g["p_emb"], rel=2e-5)          # cluster GRU, fp32 GEMM
-        _lib.call_nostream("ttr_debug_set_flags", 1)
-        try:
-            assert_rows_close(m.encode_document(x), g["p_emb"], rel=2e-5)      # generic GRU, fp32 GEMM
-        finally:
-            _lib.call_nostream("ttr_debug_set_flags", 0)
+        # tcgen05 recurrence (fp16 matmul inputs, fp32 state) on top of the fp32 GEMM: its own error
+        e = assert_rows_close(m.encode_document(x), g["p_emb"], rel=2e-4)
+        print(f"\n[cfgdims] tcgen05 GRU + fp32 GEMM: relative row error {e:.3e}")
+        for flag in (1024, 1):                                     # fp32 cluster GRU, generic GRU
+            _lib.call_nostream("ttr_debug_set_flags", flag)
+            try:
+                assert_rows_close(m.encode_document(x), g["p_emb"], rel=2e-5)
+            finally:
+                _lib.call_nostream("ttr_debug_set_flags", 0)
 
 
 def test_larger_batch_vs_oracle_at_config_dims(cuda_device):
@@ -118,6 +121,26 @@ def test_unnormalised_and_unidirectional(cuda_device):
         out = m.encode_document(torch.tensor(g["n"], device=cuda_device))
     assert_rows_close(out, g["n_emb"])
     assert (torch.linalg.vector_norm(out, dim=1) - 1).abs().max() > 1e-3
+
+
+def test_tcgen05_gru_is_repeatable_and_matches_fp32_kernel(cuda_device):
+    """Multi-tile batch (two 256-row cluster tiles, both chains, partial last chain): the tcgen05
+    recurrence must be bit-repeatable run to run (a protocol race shows up as run-to-run noise) and
+    agree with the fp32 CUDA-core cluster kernel within the fp16-operand rounding."""
+    cfg = synth.default_config(vocab_size=5000, embed_dim=200)
+    m = model_from_numpy(cfg, synth.make_state_dict(cfg, seed=5, table_seed=6), cuda_device).eval()
+    ids, _ = synth.make_tokens(500, "passage", 5000, seed=31)
+    x = torch.tensor(ids, device=cuda_device)
+    with torch.no_grad():
+        runs = [m.encode_document(x) for _ in range(4)]
+        _lib.call_nostream("ttr_debug_set_flags", 1024)
+        try:
+            ref = m.encode_document(x)
+        finally:
+            _lib.call_nostream("ttr_debug_set_flags", 0)
+    for r in runs[1:]:
+        assert torch.equal(r, runs[0])
+    assert_rows_close(runs[0], ref.cpu().numpy(), rel=2e-4)
 
 
 def test_bulk_encode_matches_per_batch_encode(cuda_device):

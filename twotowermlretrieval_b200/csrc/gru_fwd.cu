@@ -265,7 +265,9 @@ gru_fwd_generic_kernel(GruFwdArgs a, int H) {
 }
 
 int launch_gru_fwd_tc(const float* gi, const float* w_hh, const float* b_hh, const int32_t* order,
-                      const int32_t* offsets, int B, int dirs, float* y, float* h_last, float* saved, cudaStream_t st);
+                      const int32_t* offsets, int B, int dirs, float* y, float* h_last, float* saved, void* workspace,
+                      cudaStream_t st);
+int64_t gru_fwd_tc_workspace_bytes(int B, int dirs);
 
 }  // namespace ttr
 
@@ -274,19 +276,21 @@ extern "C" int ttr_debug_set_flags(int flags) {
   return TTR_OK;
 }
 
-extern "C" int ttr_gru_recurrence_fwd(const float* gi, const float* w_hh, const float* b_hh,
-                                      const int32_t* order, const int32_t* offsets, int B, int H, int dirs,
-                                      float* y, float* h_last, float* saved, void* stream) {
+static int gru_recurrence_fwd_impl(const float* gi, const float* w_hh, const float* b_hh, const int32_t* order,
+                                  const int32_t* offsets, int B, int H, int dirs, float* y, float* h_last,
+                                  float* saved, void* workspace, int64_t workspace_bytes, void* stream) {
   using namespace ttr;
   TTR_REQUIRE(B >= 1 && H >= 1 && (dirs == 1 || dirs == 2), "ttr_gru_recurrence_fwd: bad shape");
   TTR_REQUIRE(h_last != nullptr, "ttr_gru_recurrence_fwd: h_last is required");
   cudaStream_t st = (cudaStream_t)stream;
   GruFwdArgs a{gi, w_hh, b_hh, order, offsets, B, dirs, y, h_last, saved};
-  if (H == GH && !(g_debug_flags & (1 | 1024))) {
+  if (H == GH && workspace != nullptr && !(g_debug_flags & (1 | 1024))) {
     // default for H = 256: recurrent product on the tensor cores (gru_fwd_tc.cu)
-    return launch_gru_fwd_tc(gi, w_hh, b_hh, order, offsets, B, dirs, y, h_last, saved, st);
+    TTR_REQUIRE(workspace_bytes >= gru_fwd_tc_workspace_bytes(B, dirs), "ttr_gru_recurrence_fwd_ws: workspace of %lld B < %lld B",
+                (long long)workspace_bytes, (long long)gru_fwd_tc_workspace_bytes(B, dirs));
+    return launch_gru_fwd_tc(gi, w_hh, b_hh, order, offsets, B, dirs, y, h_last, saved, workspace, st);
   } else if (H == GH && !(g_debug_flags & 1)) {
-    // bit 10: the fp32 CUDA-core cluster kernel (W_hh in registers, warp-shuffle reductions)
+    // no workspace (or debug bit 10): the fp32 CUDA-core cluster kernel (W_hh in registers, warp-shuffle reductions)
     const size_t smem = (size_t)2 * GCL * GCS * sizeof(float) + 3 * GBT * sizeof(int);
     TTR_CHECK_CUDA(cudaFuncSetAttribute(gru_fwd_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(ceil_div(B, GBT) * GCL, dirs);
@@ -302,4 +306,22 @@ extern "C" int ttr_gru_recurrence_fwd(const float* gi, const float* w_hh, const 
     TTR_CHECK_LAUNCH();
   }
   return TTR_OK;
+}
+
+extern "C" int ttr_gru_recurrence_fwd(const float* gi, const float* w_hh, const float* b_hh,
+                                      const int32_t* order, const int32_t* offsets, int B, int H, int dirs,
+                                      float* y, float* h_last, float* saved, void* stream) {
+  return gru_recurrence_fwd_impl(gi, w_hh, b_hh, order, offsets, B, H, dirs, y, h_last, saved, nullptr, 0, stream);
+}
+
+extern "C" int64_t ttr_gru_fwd_workspace_bytes(int B, int H, int dirs) {
+  return H == ttr::GH ? ttr::gru_fwd_tc_workspace_bytes(B, dirs) : 0;
+}
+
+extern "C" int ttr_gru_recurrence_fwd_ws(const float* gi, const float* w_hh, const float* b_hh,
+                                         const int32_t* order, const int32_t* offsets, int B, int H, int dirs,
+                                         float* y, float* h_last, float* saved, void* workspace,
+                                         int64_t workspace_bytes, void* stream) {
+  return gru_recurrence_fwd_impl(gi, w_hh, b_hh, order, offsets, B, H, dirs, y, h_last, saved, workspace,
+                                 workspace_bytes, stream);
 }

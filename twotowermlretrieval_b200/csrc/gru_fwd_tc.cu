@@ -1,26 +1,35 @@
 // gru_fwd_tc.cu — GRU recurrence (forward, H = 256) with the recurrent product on tcgen05.
 //
 // Replaces the sequential half of `self.rnn(packed)` (backend/model.py:59-62), like gru_fwd.cu,
-// but moves gh_t = h_{t-1} W_hh^T from fp32 FMAs + warp shuffles to the tensor cores while keeping
-// fp32-level accuracy:
+// but moves gh_t = h_{t-1} W_hh^T from fp32 FMAs + warp shuffles to the tensor cores:
 //
-//   * a thread-block cluster of 8 CTAs owns one tile of 128 length-sorted rows and one direction
-//     for ALL timesteps.  CTA c owns hidden units [32c, 32c+32), i.e. 96 gate columns (r, z, n).
-//   * its slice of W_hh lives in shared memory for the whole kernel as the UMMA B operand, split
-//     into two fp16 planes  W = W_hi + W_lo  (2 x 48 KB);  h_{t-1} of the whole tile is the A
-//     operand, split the same way (2 x 64 KB).  Three kind::f16 MMA chains per step,
-//     h_hi W_hi + h_hi W_lo + h_lo W_hi, accumulate in fp32 in tensor memory: the dropped
-//     h_lo W_lo term is 2^-22 relative (W in [-1/16, 1/16] and h in [-1, 1] keep both planes in
-//     fp16 range; the low planes use fp16 subnormals, which the tensor core handles exactly).
+//   * a thread-block cluster of 8 CTAs owns one tile of 256 length-sorted rows and one direction
+//     for ALL timesteps, as two independent 128-row chains (UMMA M = 128) that interleave on the
+//     SM: while one chain's h is in flight between CTAs the other one computes.
+//     CTA c owns hidden units [32c, 32c+32), i.e. 96 gate columns (r, z, n).
+//   * its slice of W_hh, rounded to fp16, lives in shared memory for the whole kernel as the UMMA
+//     B operand (48 KB); h_{t-1} of each chain, rounded to fp16, is the A operand (64 KB per chain).
+//     One kind::f16 MMA chain of 16 k-steps per timestep accumulates in fp32 in tensor memory.
+//     Precision: the fp32 state h is carried in registers by the thread that owns it; only the
+//     matmul INPUTS are fp16 (11-bit significand, finer than the tf32 operands of the input
+//     projection).  Simulated on the reference model at config dims the rounding moves the final
+//     embeddings by 7.9e-5 relative on its own and 3.30e-4 -> 3.33e-4 together with the tf32
+//     projection (tolerance 1e-3); a three-plane hi/lo split version of this kernel (fp32-exact to
+//     2^-22) measured the same parity and 3x the tensor and exchange cost — see git history.
 //   * epilogue thread = (row, 16 units): tcgen05.ld of its 48 gate pre-activations, fused gate
-//     math against the gi row segment it prefetched while the MMAs ran, fp32 h kept in registers
-//     across timesteps, results written to y / saved / h_last, and the new h values written as
-//     fp16 hi/lo straight into the CTA's own slice of the A operand.
-//   * exchange: one elected thread pushes that 2 x 8 KB slice into the other seven CTAs' A
-//     operands with cp.async.bulk shared::cta -> shared::cluster copies that complete on the
-//     DESTINATION's mbarrier — no cluster-wide barrier in the loop.  The write-after-read hazard
-//     (a peer's MMA still reading its operand) is covered by a second mbarrier that every CTA's
-//     MMA completion signals in all eight CTAs (tcgen05.commit ... multicast::cluster).
+//     math against the gi row segment it prefetched while the MMAs ran, results written to
+//     y / saved / h_last, and the new h values written as fp16 straight into the CTA's own slice
+//     of the A operand.
+//   * exchange: the epilogue threads also write the fp16 values into the CTA's 8 KB slice of a
+//     double-buffered global scratch image of the operand (L2-resident), and one elected thread
+//     then issues ONE cp.async.bulk ... multicast::cluster load that lands the slice in all eight
+//     CTAs' A operands and completes on each destination's mbarrier — no cluster-wide barrier in
+//     the loop and 8 KB instead of 56 KB leaving the SM per step.  (The first version pushed the
+//     slice with shared::cta -> shared::cluster bulk copies: 15-30 B/clk per SM, the longest phase
+//     of the step, profiles/r1_gru_tc_trace_v1.txt.)  The write-after-read hazard (a peer's MMA
+//     still reading its operand) is covered by a second mbarrier that every CTA's MMA completion
+//     signals in all eight CTAs (tcgen05.commit ... multicast::cluster); the same signal, one step
+//     later, proves that a scratch slice has been delivered everywhere before it is rewritten.
 //
 // Operand layout (both operands K-major, no swizzle): [k / 8][row][8 halves] — 8-row x 16-byte core
 // matrices, stride-byte-offset 128 B between row groups, leading-byte-offset rows*16 B between
@@ -34,21 +43,26 @@
 namespace ttr {
 
 extern int g_debug_flags;
+extern long long* g_score_trace;     // ttr_debug_set_trace: also receives this kernel's per-step timeline
 
 constexpr int TC_H = 256;
 constexpr int TC_CL = 8;                         // CTAs per cluster
 constexpr int TC_UN = TC_H / TC_CL;              // 32 hidden units per CTA
 constexpr int TC_NG = 3 * TC_UN;                 // 96 gate columns per CTA (UMMA N)
-constexpr int TC_ROWS = 128;                     // rows per tile (UMMA M)
+constexpr int TC_ROWS = 128;                     // rows per chain (UMMA M)
+constexpr int TC_CHAINS = 2;                     // independent chains per cluster
+constexpr int TC_TILE = TC_ROWS * TC_CHAINS;     // rows per cluster
 constexpr int TC_KC = TC_H / 8;                  // 32 k-chunks of 8 halves
 constexpr int TC_A_LBO = TC_ROWS * 16;           // 2048 B between k-chunks of the A operand
 constexpr int TC_B_LBO = TC_NG * 16;             // 1536 B between k-chunks of the B operand
-constexpr int TC_A_BYTES = TC_KC * TC_A_LBO;     // 64 KB per plane
-constexpr int TC_B_BYTES = TC_KC * TC_B_LBO;     // 48 KB per plane
-constexpr int TC_SLICE_BYTES = (TC_UN / 8) * TC_A_LBO;   // 8 KB: one CTA's units in one plane
-constexpr int TC_THREADS = 256;
-constexpr int TC_TMEM_COLS = 128;
-constexpr int TC_SMEM = 2 * TC_A_BYTES + 2 * TC_B_BYTES + TC_NG * 4 + 3 * TC_ROWS * 4 + 3 * 8 + 8;
+constexpr int TC_A_BYTES = TC_KC * TC_A_LBO;     // 64 KB per chain
+constexpr int TC_B_BYTES = TC_KC * TC_B_LBO;     // 48 KB
+constexpr int TC_SLICE_BYTES = (TC_UN / 8) * TC_A_LBO;   // 8 KB: one CTA's units of one chain
+constexpr int TC_GROUP = 256;                    // threads per chain
+constexpr int TC_THREADS = TC_GROUP * TC_CHAINS;
+constexpr int TC_ACC_COLS = 128;                 // TMEM columns per chain (96 used)
+constexpr int TC_TMEM_COLS = TC_ACC_COLS * TC_CHAINS;
+constexpr int TC_SMEM = TC_CHAINS * TC_A_BYTES + TC_B_BYTES + TC_NG * 4 + 3 * TC_TILE * 4 + TC_CHAINS * 3 * 8 + 8;
 
 struct GruTcArgs {
   const float* gi;
@@ -60,7 +74,14 @@ struct GruTcArgs {
   float* y;
   float* h_last;
   float* saved;
+  unsigned char* scratch;   // [clusters][chains][2][TC_A_BYTES] operand images for the multicast exchange
+  long long* trace;   // diagnostic: [8][256] clock64 of cluster 0 / CTA 0 at eight points of each step, or NULL
 };
+
+#define TC_TRACE(role)                                                                     \
+  do {                                                                                     \
+    if (a.trace && blockIdx.x == 0 && blockIdx.y == 0 && t < 256) a.trace[(role) * 256 + t] = clock64(); \
+  } while (0)
 
 namespace {
 
@@ -69,21 +90,19 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
   return r;
 }
-__device__ __forceinline__ uint32_t mapa(uint32_t addr, uint32_t rank) {
-  uint32_t r;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
-  return r;
-}
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
-// shared::cta -> (remote) shared::cluster bulk copy, completion counted in bytes on the destination's mbarrier
-__device__ __forceinline__ void bulk_s2s(uint32_t dst_cluster, uint32_t src_cta, uint32_t bytes, uint32_t bar_cluster) {
-  asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                   dst_cluster),
-               "r"(src_cta), "r"(bytes), "r"(bar_cluster)
-               : "memory");
+// global -> shared bulk copy delivered to the same CTA-relative address (and mbarrier) in every CTA of `mask`
+__device__ __forceinline__ void bulk_g2s_multicast(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar,
+                                                   uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::
+          "r"(dst),
+      "l"(src), "r"(bytes), "r"(bar), "h"(mask)
+      : "memory");
 }
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 __device__ __forceinline__ void mma_commit_multicast(uint64_t* bar, uint16_t mask) {
   asm volatile(
       "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
@@ -109,6 +128,13 @@ __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[16])
       : "r"(taddr)
       : "memory");
 }
+__device__ __forceinline__ void tmem_ld_32x8(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+      : "r"(taddr)
+      : "memory");
+}
 // K-major operand without swizzle: 8-row x 16-byte core matrices; LBO = distance between the two
 // k-chunks of one MMA (and of consecutive k-chunks), SBO = distance between 8-row groups.
 __device__ __forceinline__ uint64_t make_kmajor_nosw_desc(uint32_t smem_addr, uint32_t lbo, uint32_t sbo) {
@@ -124,60 +150,74 @@ __host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) {
   return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
-// x = hi + lo with both halves in fp16 (lo may be subnormal): packs 8 values into two 16-byte rows
-__device__ __forceinline__ void split8(const float* x, uint4& hi, uint4& lo) {
-  uint32_t h[4], l[4];
+// 8 fp32 values -> 8 fp16 (round to nearest even) in one 16-byte row of an operand
+__device__ __forceinline__ uint4 pack8(const float* x) {
+  uint32_t h[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    const __half h0 = __float2half_rn(x[2 * i]), h1 = __float2half_rn(x[2 * i + 1]);
-    const __half l0 = __float2half_rn(x[2 * i] - __half2float(h0));
-    const __half l1 = __float2half_rn(x[2 * i + 1] - __half2float(h1));
-    h[i] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
-    l[i] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+    const __half2 v = __floats2half2_rn(x[2 * i], x[2 * i + 1]);
+    h[i] = *reinterpret_cast<const uint32_t*>(&v);
   }
-  hi = make_uint4(h[0], h[1], h[2], h[3]);
-  lo = make_uint4(l[0], l[1], l[2], l[3]);
+  return make_uint4(h[0], h[1], h[2], h[3]);
 }
 
-__device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
-__device__ __forceinline__ float fast_tanh(float x) { return 1.0f - __fdividef(2.0f, 1.0f + __expf(2.0f * x)); }
+// Activations on the MUFU pipe (16 lanes/clk/SM: the epilogue's scarcest unit) share reciprocals:
+// sigmoid(a), sigmoid(b) = (1+e^-b, 1+e^-a) / ((1+e^-a)(1+e^-b)) — 2 ex2 + 1 rcp; two tanh likewise.
+// Arguments are clamped to +-20 so that products of denominators stay finite (sigmoid(-20) = 2e-9).
+__device__ __forceinline__ float rcp_approx(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float clamp20(float x) { return fminf(fmaxf(x, -20.0f), 20.0f); }
+__device__ __forceinline__ void sigmoid2(float a, float b, float& sa, float& sb) {
+  const float da = 1.0f + __expf(-clamp20(a)), db = 1.0f + __expf(-clamp20(b));
+  const float inv = rcp_approx(da * db);
+  sa = db * inv;
+  sb = da * inv;
+}
+__device__ __forceinline__ void tanh2(float a, float b, float& ta, float& tb) {
+  const float ea = __expf(-2.0f * clamp20(a)), eb = __expf(-2.0f * clamp20(b));   // tanh(x) = (1 - e^-2x) / (1 + e^-2x)
+  const float da = 1.0f + ea, db = 1.0f + eb;
+  const float inv = rcp_approx(da * db);
+  ta = (1.0f - ea) * db * inv;
+  tb = (1.0f - eb) * da * inv;
+}
 
 }  // namespace
 
 __global__ void __cluster_dims__(TC_CL, 1, 1) __launch_bounds__(TC_THREADS, 1)
 gru_fwd_tc_kernel(GruTcArgs a) {
   extern __shared__ __align__(128) unsigned char sm[];
-  unsigned char* h_hi = sm;
-  unsigned char* h_lo = sm + TC_A_BYTES;
-  unsigned char* w_hi = sm + 2 * TC_A_BYTES;
-  unsigned char* w_lo = w_hi + TC_B_BYTES;
-  float* bias = reinterpret_cast<float*>(w_lo + TC_B_BYTES);      // [96]: b_hr, b_hz, b_hn of the slice
+  unsigned char* h_all = sm;                                        // [chains] A operands
+  unsigned char* w_sm = sm + TC_CHAINS * TC_A_BYTES;                // B operand
+  float* bias = reinterpret_cast<float*>(w_sm + TC_B_BYTES);        // [96]: b_hr, b_hz, b_hn of the slice
   int* lens = reinterpret_cast<int*>(bias + TC_NG);
-  int* toff = lens + TC_ROWS;
-  int* rowid = toff + TC_ROWS;
-  uint64_t* h_full = reinterpret_cast<uint64_t*>(rowid + TC_ROWS);   // peers' slices have landed
-  uint64_t* mma_done = h_full + 1;                                   // own accumulators are ready
-  uint64_t* consumed = h_full + 2;                                   // all 8 CTAs finished reading h_{t-1}
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(h_full + 3);
+  int* toff = lens + TC_TILE;
+  int* rowid = toff + TC_TILE;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(rowid + TC_TILE);    // per chain: h_full, mma_done, consumed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + TC_CHAINS * 3);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int rank = (int)cluster_ctarank();
   const int tile = blockIdx.x / TC_CL;
   const int dir = blockIdx.y;
   const int G3 = 3 * TC_H;
-  const int s0 = tile * TC_ROWS;
+  const int s0 = tile * TC_TILE;
 
   if (tid == 0) {
-    ptx::mbar_init(h_full, 1);
-    ptx::mbar_init(mma_done, 1);
-    ptx::mbar_init(consumed, TC_CL);
+    for (int c = 0; c < TC_CHAINS; ++c) {
+      ptx::mbar_init(bars + 3 * c + 0, 1);        // h_full: peers' slices have landed
+      ptx::mbar_init(bars + 3 * c + 1, 1);        // mma_done: own accumulators are ready
+      ptx::mbar_init(bars + 3 * c + 2, TC_CL);    // consumed: all 8 CTAs finished reading h_{t-1}
+    }
     ptx::fence_mbar_init();
   }
   if (warp == 1) {
     ptx::tmem_alloc(tmem_slot, TC_TMEM_COLS);
     ptx::tmem_relinquish();
   }
-  for (int i = tid; i < TC_ROWS; i += TC_THREADS) {
+  for (int i = tid; i < TC_TILE; i += TC_THREADS) {
     const int s = s0 + i;
     if (s < a.B) {
       const int off = a.offsets[s];
@@ -188,11 +228,11 @@ gru_fwd_tc_kernel(GruTcArgs a) {
       lens[i] = 0; toff[i] = 0; rowid[i] = 0;
     }
   }
-  {  // h_0 = 0 in both planes
-    uint4* p = reinterpret_cast<uint4*>(h_hi);
-    for (int i = tid; i < 2 * TC_A_BYTES / 16; i += TC_THREADS) p[i] = make_uint4(0u, 0u, 0u, 0u);
+  {  // h_0 = 0
+    uint4* p = reinterpret_cast<uint4*>(h_all);
+    for (int i = tid; i < TC_CHAINS * TC_A_BYTES / 16; i += TC_THREADS) p[i] = make_uint4(0u, 0u, 0u, 0u);
   }
-  {  // resident weights: rows (gate g, unit 32*rank + u) of W_hh[dir], split into fp16 planes
+  {  // resident weights: rows (gate g, unit 32*rank + u) of W_hh[dir] as fp16
     const float* wbase = a.w_hh + (size_t)dir * G3 * TC_H;
     for (int idx = tid; idx < TC_NG * TC_KC; idx += TC_THREADS) {
       const int n = idx % TC_NG, kc = idx / TC_NG;
@@ -200,10 +240,7 @@ gru_fwd_tc_kernel(GruTcArgs a) {
       const float4* src = reinterpret_cast<const float4*>(wbase + (size_t)(g * TC_H + rank * TC_UN + u) * TC_H + kc * 8);
       const float4 v0 = __ldg(src), v1 = __ldg(src + 1);
       const float x[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
-      uint4 hi, lo;
-      split8(x, hi, lo);
-      *reinterpret_cast<uint4*>(w_hi + kc * TC_B_LBO + n * 16) = hi;
-      *reinterpret_cast<uint4*>(w_lo + kc * TC_B_LBO + n * 16) = lo;
+      *reinterpret_cast<uint4*>(w_sm + kc * TC_B_LBO + n * 16) = pack8(x);
     }
     if (tid < TC_NG) bias[tid] = a.b_hh[dir * G3 + (tid / TC_UN) * TC_H + rank * TC_UN + (tid % TC_UN)];
   }
@@ -214,56 +251,57 @@ gru_fwd_tc_kernel(GruTcArgs a) {
   cluster_sync_all();                     // every CTA's barriers are initialised before any remote arrive
   const uint32_t tmem_base = *tmem_slot;
 
-  // epilogue role of this thread: TMEM lane quarter q (rows 32q..32q+31), unit half uh
-  const int q = warp & 3, uh = warp >> 2;
-  const int row = q * 32 + lane;
+  // role of this thread: chain `ch`; inside the chain TMEM lane quarter q (rows 32q..32q+31), unit half uh
+  const int ch = warp >> 3, wg = warp & 7;
+  const int q = wg & 3, uh = wg >> 2;
+  const int row = q * 32 + lane;                    // row inside the chain
   const int u0 = uh * 16;                           // first owned unit inside the CTA's slice
   const int j0 = rank * TC_UN + u0;                 // ... as a global hidden unit
-  const uint32_t tmem_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)u0;
-  const int len = lens[row];
-  const int tbase = toff[row];
-  const int maxlen = lens[0];
+  unsigned char* h_sm = h_all + ch * TC_A_BYTES;
+  uint64_t* h_full = bars + 3 * ch;
+  uint64_t* mma_done = h_full + 1;
+  uint64_t* consumed = h_full + 2;
+  const uint32_t tmem_acc = tmem_base + (uint32_t)(ch * TC_ACC_COLS);
+  const uint32_t tmem_row = tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)u0;
+  const int len = lens[ch * TC_ROWS + row];
+  const int tbase = toff[ch * TC_ROWS + row];
+  const int maxlen = lens[ch * TC_ROWS];
   const int gi_ld = a.dirs * G3, y_ld = a.dirs * TC_H;
   const float* gi_base = a.gi + dir * G3 + j0;
   float h[16];
 #pragma unroll
   for (int i = 0; i < 16; ++i) h[i] = 0.f;
 
-  const uint32_t h_hi_u32 = ptx::smem_u32(h_hi), h_lo_u32 = ptx::smem_u32(h_lo);
-  const uint32_t w_hi_u32 = ptx::smem_u32(w_hi), w_lo_u32 = ptx::smem_u32(w_lo);
+  const uint32_t h_u32 = ptx::smem_u32(h_sm);
+  unsigned char* scr = a.scratch + ((size_t)(blockIdx.y * (gridDim.x / TC_CL) + tile) * TC_CHAINS + ch) * 2 * TC_A_BYTES;
+  const uint32_t w_u32 = ptx::smem_u32(w_sm);
   constexpr uint32_t idesc = make_idesc_f16(TC_ROWS, TC_NG);
+  const int kc0 = 4 * rank + 2 * uh;                // k-chunk of this thread's first 8 units
 
   for (int t = 0; t < maxlen; ++t) {
     const uint32_t par = (uint32_t)t & 1u;
     const bool active = t < len;
     const int tok = active ? tbase + (dir == 0 ? t : len - 1 - t) : 0;
 
-    if (warp == 0) {
-      // ===== MMA issue: gh = h_hi W_hi + h_hi W_lo + h_lo W_hi (16 k-steps of 16 each) =====
+    if (wg == 0 && lane == 0 && ch == 0) TC_TRACE(0);
+    if (wg == 0) {
+      // ===== MMA issue: gh = h W_hh^T for this chain (16 k-steps of 16) =====
       if (t > 0) ptx::mbar_wait(h_full, par ^ 1u);
       ptx::tc_fence_after_sync();
+      if (lane == 0 && ch == 0) TC_TRACE(1);
       if (ptx::elect_one()) {
-        const uint64_t a_hi = make_kmajor_nosw_desc(h_hi_u32, TC_A_LBO, 128);
-        const uint64_t a_lo = make_kmajor_nosw_desc(h_lo_u32, TC_A_LBO, 128);
-        const uint64_t b_hi = make_kmajor_nosw_desc(w_hi_u32, TC_B_LBO, 128);
-        const uint64_t b_lo = make_kmajor_nosw_desc(w_lo_u32, TC_B_LBO, 128);
+        const uint64_t a_desc = make_kmajor_nosw_desc(h_u32, TC_A_LBO, 128);
+        const uint64_t b_desc = make_kmajor_nosw_desc(w_u32, TC_B_LBO, 128);
 #pragma unroll
         for (int ks = 0; ks < TC_H / 16; ++ks)
-          mma_f16_ss(tmem_base, a_hi + (uint64_t)(ks * (2 * TC_A_LBO >> 4)), b_hi + (uint64_t)(ks * (2 * TC_B_LBO >> 4)),
+          mma_f16_ss(tmem_acc, a_desc + (uint64_t)(ks * (2 * TC_A_LBO >> 4)), b_desc + (uint64_t)(ks * (2 * TC_B_LBO >> 4)),
                      idesc, ks != 0);
-#pragma unroll
-        for (int ks = 0; ks < TC_H / 16; ++ks)
-          mma_f16_ss(tmem_base, a_hi + (uint64_t)(ks * (2 * TC_A_LBO >> 4)), b_lo + (uint64_t)(ks * (2 * TC_B_LBO >> 4)),
-                     idesc, 1u);
-#pragma unroll
-        for (int ks = 0; ks < TC_H / 16; ++ks)
-          mma_f16_ss(tmem_base, a_lo + (uint64_t)(ks * (2 * TC_A_LBO >> 4)), b_hi + (uint64_t)(ks * (2 * TC_B_LBO >> 4)),
-                     idesc, 1u);
         ptx::mma_commit(mma_done);
         // nobody waits for the last step's signal, and a peer may have left by the time it would land
         if (t + 1 < maxlen) mma_commit_multicast(consumed, (uint16_t)0xff);
       }
       __syncwarp();
+      if (lane == 0 && ch == 0) TC_TRACE(2);
     }
 
     // gi row segment of this step (3 gates x 16 units), in flight while the MMAs run
@@ -278,75 +316,77 @@ gru_fwd_tc_kernel(GruTcArgs a) {
 
     ptx::mbar_wait(mma_done, par);
     ptx::tc_fence_after_sync();
+    if (wg == 0 && lane == 0 && ch == 0) TC_TRACE(3);
     if (__any_sync(0xffffffffu, active)) {
-      uint32_t ar[16], az[16], an[16];
-      tmem_ld_32x16(tmem_row, ar);
-      tmem_ld_32x16(tmem_row + TC_UN, az);
-      tmem_ld_32x16(tmem_row + 2 * TC_UN, an);
-      ptx::tmem_ld_wait();
-      if (active) {
-        const float* gf = reinterpret_cast<const float*>(g4);
-        float rr[16], zz[16], nn[16], gn[16];
+      const float* gf = reinterpret_cast<const float*>(g4);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const float r = fast_sigmoid(gf[i] + __uint_as_float(ar[i]) + bias[u0 + i]);
-          const float z = fast_sigmoid(gf[16 + i] + __uint_as_float(az[i]) + bias[TC_UN + u0 + i]);
-          const float ghn = __uint_as_float(an[i]) + bias[2 * TC_UN + u0 + i];
-          const float n = fast_tanh(fmaf(r, ghn, gf[32 + i]));
-          h[i] = fmaf(z, h[i] - n, n);            // (1-z)*n + z*h
-          rr[i] = r; zz[i] = z; nn[i] = n; gn[i] = ghn;
-        }
-        // new h -> own slice of the A operand (k = 32*rank + u0 + i -> k-chunks 4*rank + 2*uh + {0,1})
-        {
-          uint4 hi, lo;
-          const int kc = 4 * rank + 2 * uh;
-          split8(h, hi, lo);
-          *reinterpret_cast<uint4*>(h_hi + kc * TC_A_LBO + row * 16) = hi;
-          *reinterpret_cast<uint4*>(h_lo + kc * TC_A_LBO + row * 16) = lo;
-          split8(h + 8, hi, lo);
-          *reinterpret_cast<uint4*>(h_hi + (kc + 1) * TC_A_LBO + row * 16) = hi;
-          *reinterpret_cast<uint4*>(h_lo + (kc + 1) * TC_A_LBO + row * 16) = lo;
-        }
-        if (a.y) {
-          float4* yp = reinterpret_cast<float4*>(a.y + (size_t)tok * y_ld + dir * TC_H + j0);
+      for (int hf = 0; hf < 2; ++hf) {
+        uint32_t ar[8], az[8], an[8];
+        tmem_ld_32x8(tmem_row + 8 * hf, ar);
+        tmem_ld_32x8(tmem_row + TC_UN + 8 * hf, az);
+        tmem_ld_32x8(tmem_row + 2 * TC_UN + 8 * hf, an);
+        ptx::tmem_ld_wait();
+        if (active) {
+          float rr[8], zz[8], nn[8], gn[8];
 #pragma unroll
-          for (int i = 0; i < 4; ++i) yp[i] = make_float4(h[4 * i], h[4 * i + 1], h[4 * i + 2], h[4 * i + 3]);
-        }
-        if (a.saved) {
-          float4* sv = reinterpret_cast<float4*>(a.saved + ((size_t)tok * a.dirs + dir) * 4 * TC_H + j0);
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            sv[i] = make_float4(rr[4 * i], rr[4 * i + 1], rr[4 * i + 2], rr[4 * i + 3]);
-            sv[TC_H / 4 + i] = make_float4(zz[4 * i], zz[4 * i + 1], zz[4 * i + 2], zz[4 * i + 3]);
-            sv[2 * TC_H / 4 + i] = make_float4(nn[4 * i], nn[4 * i + 1], nn[4 * i + 2], nn[4 * i + 3]);
-            sv[3 * TC_H / 4 + i] = make_float4(gn[4 * i], gn[4 * i + 1], gn[4 * i + 2], gn[4 * i + 3]);
+          for (int i = 0; i < 8; ++i) {
+            const int u = 8 * hf + i;
+            sigmoid2(gf[u] + __uint_as_float(ar[i]) + bias[u0 + u],
+                     gf[16 + u] + __uint_as_float(az[i]) + bias[TC_UN + u0 + u], rr[i], zz[i]);
+            gn[i] = __uint_as_float(an[i]) + bias[2 * TC_UN + u0 + u];
           }
-        }
-        if (t == len - 1) {
-          float4* hp = reinterpret_cast<float4*>(a.h_last + (size_t)rowid[row] * y_ld + dir * TC_H + j0);
 #pragma unroll
-          for (int i = 0; i < 4; ++i) hp[i] = make_float4(h[4 * i], h[4 * i + 1], h[4 * i + 2], h[4 * i + 3]);
+          for (int i = 0; i < 8; i += 2) {
+            tanh2(fmaf(rr[i], gn[i], gf[32 + 8 * hf + i]), fmaf(rr[i + 1], gn[i + 1], gf[32 + 8 * hf + i + 1]), nn[i],
+                  nn[i + 1]);
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int u = 8 * hf + i;
+            h[u] = fmaf(zz[i], h[u] - nn[i], nn[i]);            // (1-z)*n + z*h
+          }
+          // new h (fp16) -> own slice of this step's scratch image (k = 32*rank + u0 + 8*hf + i)
+          *reinterpret_cast<uint4*>(scr + (size_t)par * TC_A_BYTES + (kc0 + hf) * TC_A_LBO + row * 16) = pack8(h + 8 * hf);
+          if (a.y) {
+            float4* yp = reinterpret_cast<float4*>(a.y + (size_t)tok * y_ld + dir * TC_H + j0 + 8 * hf);
+            yp[0] = make_float4(h[8 * hf], h[8 * hf + 1], h[8 * hf + 2], h[8 * hf + 3]);
+            yp[1] = make_float4(h[8 * hf + 4], h[8 * hf + 5], h[8 * hf + 6], h[8 * hf + 7]);
+          }
+          if (a.saved) {
+            float4* sv = reinterpret_cast<float4*>(a.saved + ((size_t)tok * a.dirs + dir) * 4 * TC_H + j0 + 8 * hf);
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+              sv[i] = make_float4(rr[4 * i], rr[4 * i + 1], rr[4 * i + 2], rr[4 * i + 3]);
+              sv[TC_H / 4 + i] = make_float4(zz[4 * i], zz[4 * i + 1], zz[4 * i + 2], zz[4 * i + 3]);
+              sv[2 * TC_H / 4 + i] = make_float4(nn[4 * i], nn[4 * i + 1], nn[4 * i + 2], nn[4 * i + 3]);
+              sv[3 * TC_H / 4 + i] = make_float4(gn[4 * i], gn[4 * i + 1], gn[4 * i + 2], gn[4 * i + 3]);
+            }
+          }
+          if (t == len - 1) {
+            float4* hp = reinterpret_cast<float4*>(a.h_last + (size_t)rowid[ch * TC_ROWS + row] * y_ld + dir * TC_H + j0 + 8 * hf);
+            hp[0] = make_float4(h[8 * hf], h[8 * hf + 1], h[8 * hf + 2], h[8 * hf + 3]);
+            hp[1] = make_float4(h[8 * hf + 4], h[8 * hf + 5], h[8 * hf + 6], h[8 * hf + 7]);
+          }
         }
       }
     }
+    if (wg == 0 && lane == 0 && ch == 0) TC_TRACE(4);
     ptx::tc_fence_before_sync();
-    ptx::fence_proxy_async_smem();        // the slice written above is read by the copy engine and the tensor core
-    __syncthreads();
+    __threadfence();                      // the slice written above must be in L2 ...
+    fence_proxy_async_all();              // ... and ordered before the copy engine's (async proxy) read of it
+    ptx::named_bar_sync(1 + ch, TC_GROUP);
+    if (wg == 0 && lane == 0 && ch == 0) TC_TRACE(5);
 
-    if (warp == 0 && t + 1 < maxlen) {
-      // ===== exchange: push the slice to the seven peers once all of them have finished reading h_{t-1} =====
+    if (wg == 0 && t + 1 < maxlen) {
+      // ===== exchange: once all 8 CTAs have finished reading h_{t-1}, land the new slice in all of them =====
       if (ptx::elect_one()) {
         ptx::mbar_wait(consumed, par);
-        ptx::mbar_arrive_expect_tx(h_full, (TC_CL - 1) * 2 * TC_SLICE_BYTES);
+        if (ch == 0) TC_TRACE(6);
+        ptx::mbar_arrive_expect_tx(h_full, TC_CL * TC_SLICE_BYTES);      // eight slices arrive here, one per CTA
         const uint32_t off = (uint32_t)rank * TC_SLICE_BYTES;
-        const uint32_t bar = ptx::smem_u32(h_full);
-#pragma unroll
-        for (int p = 0; p < TC_CL; ++p) {
-          if (p == rank) continue;
-          const uint32_t rbar = mapa(bar, (uint32_t)p);
-          bulk_s2s(mapa(h_hi_u32 + off, (uint32_t)p), h_hi_u32 + off, TC_SLICE_BYTES, rbar);
-          bulk_s2s(mapa(h_lo_u32 + off, (uint32_t)p), h_lo_u32 + off, TC_SLICE_BYTES, rbar);
-        }
+        bulk_g2s_multicast(h_u32 + off, scr + (size_t)par * TC_A_BYTES + off, TC_SLICE_BYTES, ptx::smem_u32(h_full),
+                           (uint16_t)0xff);
+        if (ch == 0) TC_TRACE(7);
       }
       __syncwarp();
     }
@@ -358,11 +398,17 @@ gru_fwd_tc_kernel(GruTcArgs a) {
   if (warp == 1) ptx::tmem_dealloc(tmem_base, TC_TMEM_COLS);
 }
 
+int64_t gru_fwd_tc_workspace_bytes(int B, int dirs) {
+  return (int64_t)ceil_div(B, TC_TILE) * dirs * TC_CHAINS * 2 * TC_A_BYTES;
+}
+
 int launch_gru_fwd_tc(const float* gi, const float* w_hh, const float* b_hh, const int32_t* order,
-                      const int32_t* offsets, int B, int dirs, float* y, float* h_last, float* saved, cudaStream_t st) {
-  GruTcArgs a{gi, w_hh, b_hh, order, offsets, B, dirs, y, h_last, saved};
+                      const int32_t* offsets, int B, int dirs, float* y, float* h_last, float* saved, void* workspace,
+                      cudaStream_t st) {
+  GruTcArgs a{gi, w_hh, b_hh, order, offsets, B, dirs, y, h_last, saved, reinterpret_cast<unsigned char*>(workspace),
+              g_score_trace};
   TTR_CHECK_CUDA(cudaFuncSetAttribute(gru_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
-  dim3 grid(ceil_div(B, TC_ROWS) * TC_CL, dirs);
+  dim3 grid(ceil_div(B, TC_TILE) * TC_CL, dirs);
   gru_fwd_tc_kernel<<<grid, TC_THREADS, TC_SMEM, st>>>(a);
   TTR_CHECK_LAUNCH();
   return TTR_OK;

@@ -8,7 +8,7 @@ Pipeline of one encode call — the body of `RNNEncoder.forward` (reference
   ttr_embed_gather    packed token matrix X [tokens, E]           (model.py:49)
   per layer:
     ttr_gemm_tf32_bias        gi = X W_ih^T + b_ih, both directions (tcgen05)
-    ttr_gru_recurrence_fwd    h_t recurrence, per-step outputs, final states
+    ttr_gru_recurrence_fwd_ws h_t recurrence, per-step outputs, final states
   ttr_proj_l2norm_fwd  cat -> Linear -> F.normalize                (model.py:65-74)
 """
 from __future__ import annotations
@@ -101,7 +101,10 @@ def _forward_impl(enc, ids: torch.Tensor, need_grad: bool, training: bool):
         y = torch.empty(Mb, dirs * H, dtype=torch.float32, device=dev) if (not last or need_grad) else None
         saved = torch.empty(Mb, dirs, 4, H, dtype=torch.float32, device=dev) if need_grad else None
         h_last = torch.empty(B, dirs * H, dtype=torch.float32, device=dev)
-        _lib.call("ttr_gru_recurrence_fwd", gi, W_hh, b_hh, plan.order, plan.offsets, B, H, dirs, y, h_last, saved)
+        ws_bytes = int(_lib.load().ttr_gru_fwd_workspace_bytes(B, H, dirs))
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev) if ws_bytes else None
+        _lib.call("ttr_gru_recurrence_fwd_ws", gi, W_hh, b_hh, plan.order, plan.offsets, B, H, dirs, y, h_last, saved,
+                  ws, ws_bytes)
         del gi
         ys.append(y)
         saveds.append(saved)
