@@ -161,27 +161,63 @@ __device__ __forceinline__ uint4 pack8(const float* x) {
   return make_uint4(h[0], h[1], h[2], h[3]);
 }
 
+// 4x4 transpose of 16-byte elements inside each group of 4 lanes: on entry lane c of a group holds
+// v[k] = M[k][c]; on exit it holds v[k] = M[c][k].  Used to turn "lane = row" register tiles into
+// row-contiguous global accesses: a warp-wide load where every lane reads 16 B of its own row touches 32
+// lines (32 L1 wavefronts); with lane (G, c) reading chunk c of row 4G + k it touches 8 rows x 64 B.
+__device__ __forceinline__ float4 shfl_xor_f4(const float4& v, int m) {
+  return make_float4(__shfl_xor_sync(0xffffffffu, v.x, m), __shfl_xor_sync(0xffffffffu, v.y, m),
+                     __shfl_xor_sync(0xffffffffu, v.z, m), __shfl_xor_sync(0xffffffffu, v.w, m));
+}
+__device__ __forceinline__ void transpose4(float4 (&v)[4], int lane) {
+  {
+    const bool hi = (lane & 1) != 0;
+    const float4 r0 = shfl_xor_f4(hi ? v[0] : v[1], 1);
+    const float4 r1 = shfl_xor_f4(hi ? v[2] : v[3], 1);
+    if (hi) { v[0] = r0; v[2] = r1; } else { v[1] = r0; v[3] = r1; }
+  }
+  {
+    const bool hi = (lane & 2) != 0;
+    const float4 r0 = shfl_xor_f4(hi ? v[0] : v[2], 2);
+    const float4 r1 = shfl_xor_f4(hi ? v[1] : v[3], 2);
+    if (hi) { v[0] = r0; v[1] = r1; } else { v[2] = r0; v[3] = r1; }
+  }
+}
+
 // Activations on the MUFU pipe (16 lanes/clk/SM: the epilogue's scarcest unit) share reciprocals:
 // sigmoid(a), sigmoid(b) = (1+e^-b, 1+e^-a) / ((1+e^-a)(1+e^-b)) — 2 ex2 + 1 rcp; two tanh likewise.
-// Arguments are clamped to +-20 so that products of denominators stay finite (sigmoid(-20) = 2e-9).
+// Arguments are clamped from below (-20 / -10) so that products of denominators stay finite
+// (sigmoid(-20) = 2e-9, tanh(-10) = -1 + 4e-9); large positive arguments just make e^-x vanish.
 __device__ __forceinline__ float rcp_approx(float x) {
   float r;
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
   return r;
 }
-__device__ __forceinline__ float clamp20(float x) { return fminf(fmaxf(x, -20.0f), 20.0f); }
 __device__ __forceinline__ void sigmoid2(float a, float b, float& sa, float& sb) {
-  const float da = 1.0f + __expf(-clamp20(a)), db = 1.0f + __expf(-clamp20(b));
+  const float da = 1.0f + __expf(-fmaxf(a, -20.0f)), db = 1.0f + __expf(-fmaxf(b, -20.0f));
   const float inv = rcp_approx(da * db);
   sa = db * inv;
   sb = da * inv;
 }
 __device__ __forceinline__ void tanh2(float a, float b, float& ta, float& tb) {
-  const float ea = __expf(-2.0f * clamp20(a)), eb = __expf(-2.0f * clamp20(b));   // tanh(x) = (1 - e^-2x) / (1 + e^-2x)
+  const float ea = __expf(-2.0f * fmaxf(a, -10.0f)), eb = __expf(-2.0f * fmaxf(b, -10.0f));   // tanh(x) = (1 - e^-2x) / (1 + e^-2x)
   const float da = 1.0f + ea, db = 1.0f + eb;
   const float inv = rcp_approx(da * db);
   ta = (1.0f - ea) * db * inv;
   tb = (1.0f - eb) * da * inv;
+}
+
+// per-step outputs y[tok, col0 + 16 units] of a warp's 32 rows, written row-contiguous (see transpose4)
+__device__ __forceinline__ void store_y(float* y, const float (&h)[16], const int (&tok_k)[4], int t,
+                                        const int* lens4, int y_ld, int col0, int lane) {
+  if (y == nullptr) return;
+  float4 v[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) v[k] = make_float4(h[4 * k], h[4 * k + 1], h[4 * k + 2], h[4 * k + 3]);
+  transpose4(v, lane);                         // lane (G, c) now holds units 4c..4c+3 of rows 4G + k
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+    if (t < lens4[k]) *(reinterpret_cast<float4*>(y + (size_t)tok_k[k] * y_ld + col0) + (lane & 3)) = v[k];
 }
 
 }  // namespace
@@ -198,7 +234,10 @@ gru_fwd_tc_kernel(GruTcArgs a) {
   uint64_t* bars = reinterpret_cast<uint64_t*>(rowid + TC_TILE);    // per chain: h_full, mma_done, consumed
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + TC_CHAINS * 3);
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  // warp index through a shuffle: ptxas then knows it is warp-uniform and keeps everything derived from it
+  // (chain, operand addresses, TMEM columns) in uniform registers — otherwise every tcgen05.mma operand
+  // goes through an R2UR waterfall loop (~100 cycles per MMA instead of ~60)
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = tid & 31;
   const int rank = (int)cluster_ctarank();
   const int tile = blockIdx.x / TC_CL;
   const int dir = blockIdx.y;
@@ -304,21 +343,27 @@ gru_fwd_tc_kernel(GruTcArgs a) {
       if (lane == 0 && ch == 0) TC_TRACE(2);
     }
 
-    // gi row segment of this step (3 gates x 16 units), in flight while the MMAs run
-    float4 g4[12];
-    if (active) {
-      const float4* gp = reinterpret_cast<const float4*>(gi_base + (size_t)tok * gi_ld);
+    // gi of this step (3 gates x 16 units per thread), in flight while the MMAs run.  Loaded row-contiguous:
+    // lane (G, c) reads units 4c..4c+3 of rows 4G + k (k = 0..3), transposed into place after the wait.
+    // Rows past their end read token 0 (valid memory, unused).
+    const int grp4 = lane & ~3, c4 = lane & 3;
+    int tok_k[4];
 #pragma unroll
-      for (int g = 0; g < 3; ++g)
+    for (int k = 0; k < 4; ++k) tok_k[k] = __shfl_sync(0xffffffffu, tok, grp4 + k);
+    float4 g4[3][4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) g4[g * 4 + i] = __ldg(gp + g * (TC_H / 4) + i);
-    }
+    for (int g = 0; g < 3; ++g)
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        g4[g][k] = __ldg(reinterpret_cast<const float4*>(gi_base + (size_t)tok_k[k] * gi_ld + g * TC_H) + c4);
 
     ptx::mbar_wait(mma_done, par);
     ptx::tc_fence_after_sync();
     if (wg == 0 && lane == 0 && ch == 0) TC_TRACE(3);
+#pragma unroll
+    for (int g = 0; g < 3; ++g) transpose4(g4[g], lane);
     if (__any_sync(0xffffffffu, active)) {
-      const float* gf = reinterpret_cast<const float*>(g4);
+      const float* gf = reinterpret_cast<const float*>(g4);   // [gate][16 units] of this thread's row
 #pragma unroll
       for (int hf = 0; hf < 2; ++hf) {
         uint32_t ar[8], az[8], an[8];
@@ -347,11 +392,6 @@ gru_fwd_tc_kernel(GruTcArgs a) {
           }
           // new h (fp16) -> own slice of this step's scratch image (k = 32*rank + u0 + 8*hf + i)
           *reinterpret_cast<uint4*>(scr + (size_t)par * TC_A_BYTES + (kc0 + hf) * TC_A_LBO + row * 16) = pack8(h + 8 * hf);
-          if (a.y) {
-            float4* yp = reinterpret_cast<float4*>(a.y + (size_t)tok * y_ld + dir * TC_H + j0 + 8 * hf);
-            yp[0] = make_float4(h[8 * hf], h[8 * hf + 1], h[8 * hf + 2], h[8 * hf + 3]);
-            yp[1] = make_float4(h[8 * hf + 4], h[8 * hf + 5], h[8 * hf + 6], h[8 * hf + 7]);
-          }
           if (a.saved) {
             float4* sv = reinterpret_cast<float4*>(a.saved + ((size_t)tok * a.dirs + dir) * 4 * TC_H + j0 + 8 * hf);
 #pragma unroll
@@ -362,11 +402,6 @@ gru_fwd_tc_kernel(GruTcArgs a) {
               sv[3 * TC_H / 4 + i] = make_float4(gn[4 * i], gn[4 * i + 1], gn[4 * i + 2], gn[4 * i + 3]);
             }
           }
-          if (t == len - 1) {
-            float4* hp = reinterpret_cast<float4*>(a.h_last + (size_t)rowid[ch * TC_ROWS + row] * y_ld + dir * TC_H + j0 + 8 * hf);
-            hp[0] = make_float4(h[8 * hf], h[8 * hf + 1], h[8 * hf + 2], h[8 * hf + 3]);
-            hp[1] = make_float4(h[8 * hf + 4], h[8 * hf + 5], h[8 * hf + 6], h[8 * hf + 7]);
-          }
         }
       }
     }
@@ -376,6 +411,16 @@ gru_fwd_tc_kernel(GruTcArgs a) {
     fence_proxy_async_all();              // ... and ordered before the copy engine's (async proxy) read of it
     ptx::named_bar_sync(1 + ch, TC_GROUP);
     if (wg == 0 && lane == 0 && ch == 0) TC_TRACE(5);
+    // the exchange is issued first (below, by one thread of warp 0); the per-step outputs leave after the
+    // fence so that it only waits for the 32 bytes of scratch per thread, not for the HBM writes
+    if (wg != 0) store_y(a.y, h, tok_k, t, lens + ch * TC_ROWS + q * 32 + grp4, y_ld, dir * TC_H + j0, lane);
+    if (active && wg != 0) {
+      if (t == len - 1) {
+        float4* hp = reinterpret_cast<float4*>(a.h_last + (size_t)rowid[ch * TC_ROWS + row] * y_ld + dir * TC_H + j0);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) hp[i] = make_float4(h[4 * i], h[4 * i + 1], h[4 * i + 2], h[4 * i + 3]);
+      }
+    }
 
     if (wg == 0 && t + 1 < maxlen) {
       // ===== exchange: once all 8 CTAs have finished reading h_{t-1}, land the new slice in all of them =====
@@ -389,6 +434,14 @@ gru_fwd_tc_kernel(GruTcArgs a) {
         if (ch == 0) TC_TRACE(7);
       }
       __syncwarp();
+    }
+    if (wg == 0) store_y(a.y, h, tok_k, t, lens + ch * TC_ROWS + q * 32 + grp4, y_ld, dir * TC_H + j0, lane);
+    if (active && wg == 0) {
+      if (t == len - 1) {
+        float4* hp = reinterpret_cast<float4*>(a.h_last + (size_t)rowid[ch * TC_ROWS + row] * y_ld + dir * TC_H + j0);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) hp[i] = make_float4(h[4 * i], h[4 * i + 1], h[4 * i + 2], h[4 * i + 3]);
+      }
     }
   }
 
@@ -415,3 +468,19 @@ int launch_gru_fwd_tc(const float* gi, const float* w_hh, const float* b_hh, con
 }
 
 }  // namespace ttr
+
+// diagnostic: how many 8-CTA clusters of the tcgen05 recurrence the device can hold at once
+extern "C" int ttr_debug_gru_tc_max_clusters(int* out) {
+  using namespace ttr;
+  TTR_CHECK_CUDA(cudaFuncSetAttribute(gru_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(TC_CL * 64, 1, 1);
+  cfg.blockDim = dim3(TC_THREADS, 1, 1);
+  cfg.dynamicSmemBytes = TC_SMEM;
+  cudaLaunchAttribute attr;
+  attr.id = cudaLaunchAttributeClusterDimension;
+  attr.val.clusterDim.x = TC_CL; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+  cfg.attrs = &attr; cfg.numAttrs = 1;
+  TTR_CHECK_CUDA(cudaOccupancyMaxActiveClusters(out, gru_fwd_tc_kernel, &cfg));
+  return TTR_OK;
+}
