@@ -338,18 +338,24 @@ def extras(index, dev, world, rank, timed, hbm_peak):
         model.doc_encoder.embedding.weight.requires_grad_(False)
         model.to(dev).eval()
         model.doc_encoder.strict_lengths = False
-        ids, lens = synth.make_tokens(8192, "passage", cfg["VOCAB_SIZE"], seed=2 + rank)
+        # 7,680 rows = 30 cluster tiles x 2 directions = 4 full waves of the 15 eight-CTA clusters a B200 holds
+        NP, BS = 15360, 7680
+        ids, lens = synth.make_tokens(NP, "passage", cfg["VOCAB_SIZE"], seed=2 + rank)
         order = np.argsort(-lens, kind="stable")
-        batches = [torch.tensor(ids[order[i:i + 2048], :int(lens[order[i]])], device=dev) for i in range(0, 8192, 2048)]
+        batches = [torch.tensor(ids[order[i:i + BS], :int(lens[order[i]])], device=dev) for i in range(0, NP, BS)]
         with torch.no_grad():
             for b in batches:
                 model.encode_document(b)
             ms = timed(lambda s: [model.encode_document(b) for b in batches], 3)
         toks = int(lens.sum())
-        out["doc_encode"] = {"passages_per_s": 8192 * world / (ms * 1e-3), "tokens_per_s": toks * world / (ms * 1e-3),
-                             "ms_per_8192_passages": ms, "mean_len": float(lens.mean()),
+        proj_flops = toks * 2_187_264.0          # input-projection GEMMs, both layers and directions
+        out["doc_encode"] = {"passages_per_s": NP * world / (ms * 1e-3), "tokens_per_s": toks * world / (ms * 1e-3),
+                             "ms_per_15360_passages": ms, "mean_len": float(lens.mean()),
+                             "whole_tower_tflops": toks * 3_760_128.0 / (ms * 1e-3) / 1e12,
+                             "projection_flop_share_tflops": proj_flops / (ms * 1e-3) / 1e12,
                              "config": "GRU 2-layer bidirectional H=256 E=200 V=400005 (backend/config.json), "
-                                       "length-sorted batches of 2048 passages, device-resident ids"}
+                                       "length-sorted batches of 7680 passages, device-resident ids; recurrence on "
+                                       "tcgen05 (fp16 operands, fp32 state), projections tcgen05 tf32"}
     except Exception as e:  # secondary measurement must never kill the headline line
         out["doc_encode"] = {"error": repr(e)}
     return out

@@ -130,6 +130,13 @@ int ttr_embed_scatter_grad(const int64_t* ids, int B, int T, int64_t V, int E,
 /* out[N] (+)= column sums of A[m_valid, N] (b_ih / b_hh / projection-bias gradients). */
 int ttr_colsum(const float* A, int m_bound, const int32_t* m_valid, int N, float* out,
                int accumulate, void* stream);
+/* Rank of document target[q] among all N documents for query q (1 = best; -1 if target is out of
+ * range): 1 + #{j : s_qj > s_qt or (s_qj == s_qt and j < t)} — the position `torch.sort(descending)`
+ * + search gives in BatchEvaluator.evaluate (backend/evaluators.py:49-73), from one streaming pass
+ * without the [B, N] matrix.  Q fp32 [B, D], docs fp32 [N, D], D % 4 == 0; score_out (optional)
+ * receives s_qt. */
+int ttr_positive_rank(const float* Q, const float* docs, const int64_t* target, int B, int64_t N, int D,
+                      int32_t* rank_out, float* score_out, void* stream);
 /* Test/debug switches: bit0 = force the generic (any-H) GRU kernels, bit1 = encode TMA maps
  * as FLOAT32 instead of TFLOAT32 (hardware truncation instead of round-to-nearest),
  * bit2 = force the CUDA-core streaming scorer for every batch size, bit8 = no sample pass,

@@ -198,6 +198,91 @@ def case_inferencer_hybrid():
     print("inferencer/hybrid ok", res_idx[0][:5])
 
 
+def case_artifacts_eval():
+    """Run the reference artefact writer (`backend/main.py:92-153`), `BatchEvaluator` and
+    `CorpusEvaluator` (`backend/evaluators.py:9-209`) on a synthetic triplet set at H = 256, and the
+    reference `QueryInferencer` on the directory the writer produced.  `backend/main.py` imports
+    `data_loader` -> `fastparquet` (absent here): an empty stub module named `fastparquet` is put into
+    `sys.modules` for the import; none of the functions exercised touches it."""
+    import random
+    import types
+    sys.modules.setdefault("fastparquet", types.ModuleType("fastparquet"))
+    os.environ.setdefault("WANDB_MODE", "disabled")
+    import main as ref_main                      # /root/reference/backend/main.py, unmodified
+    import evaluators as ref_eval
+    words = ["the", "machine", "learning", "deep", "neural", "network", "data", "text", "image", "video",
+             "language", "natural", "vision", "computer", "model", "layer", "search", "query", "document",
+             "retrieval", "vector", "index", "tower", "embedding", "train", "loss", "cosine", "score",
+             "rank", "passage", "and", "of", "in", ".", ",", "?"]
+    w2i = {w: i for i, w in enumerate(words)}
+    cfg = {"HIDDEN_DIM": 256, "RNN_TYPE": "GRU", "NUM_LAYERS": 1, "BIDIRECTIONAL": True, "DROPOUT": 0.0,
+           "MARGIN": 0.5, "NORMALIZE_OUTPUT": True, "EMBED_DIM": 12, "BATCH_SIZE": 64}
+    rng = np.random.default_rng(91)
+    pool = [" ".join(rng.choice(words[1:33], size=int(rng.integers(5, 16)))) + " ." for _ in range(90)]
+    queries = [" ".join(rng.choice(words[1:30], size=int(rng.integers(2, 6)))) for _ in range(36)]
+    triplets = []
+    pos_order = rng.permutation(90)                       # every positive is used once: BatchEvaluator's rank of a
+    for qi, q in enumerate(queries):                      # duplicated positive would hinge on torch.sort's tie order
+        for _ in range(int(rng.integers(1, 3))):          # several positives per query
+            triplets.append((q, pool[int(pos_order[len(triplets)])], pool[int(rng.integers(0, 90))]))
+    val = triplets[: len(triplets) // 2]
+    with tempfile.TemporaryDirectory() as td:
+        td = Path(td)
+        art = td / "artifacts" / "run-y"
+        (td / "frontend").mkdir()
+        (td / "frontend" / "config.json").write_text(json.dumps({"ARTIFACTS_PATH": str(art)}))
+        w2i_path = td / "word_to_idx.pkl"
+        with open(w2i_path, "wb") as f:
+            pickle.dump(w2i, f)
+        import tokenizer as ref_tok
+        tok = ref_tok.PretrainedTokenizer(str(w2i_path))
+        full = dict(cfg, VOCAB_SIZE=tok.vocab_size())
+        sd = synth.make_state_dict(full, seed=31, table_seed=32)
+        model, _ = ref_model(full, sd, True)
+        model.device = torch.device("cpu")
+        run_cfg = dict(cfg, WORD_TO_IDX_PATH=str(w2i_path))
+        ref_main.save_inference_artifacts(art, model, run_cfg, tok, {"train": triplets, "validation": val})
+        with open(art / "documents.pkl", "rb") as f:
+            documents = pickle.load(f)
+        doc_emb = np.load(art / "document_embeddings.npy")
+        with open(art / "tfidf_artifacts.pkl", "rb") as f:
+            tf = pickle.load(f)
+        mat = tf["matrix"].tocsr()
+        mat.sort_indices()
+        vocab = tf["vectorizer"].vocabulary_
+        saved_cfg = json.loads((art / "config.json").read_text())
+        state_keys = list(torch.load(art / "model.pth").keys())
+        # evaluators
+        loader = torch.utils.data.DataLoader(ref_main.TripletDataset(val, tok), batch_size=16, shuffle=False,
+                                             collate_fn=ref_main.collate_fn)
+        bm, bl = ref_eval.BatchEvaluator(top_k=[1, 5, 10]).evaluate(model, loader, torch.device("cpu"), full)
+        random.seed(1234)
+        # defaults (max_candidates=1000, max_queries=50) exceed the set sizes: nothing is sub-sampled, so the
+        # result does not depend on the per-process string hash order of `list(set(...))`
+        cm = ref_eval.CorpusEvaluator(top_k=[1, 5, 10]).evaluate(
+            model, val, tok, torch.device("cpu"))
+        # the reference reader on the directory the reference writer produced
+        cwd = os.getcwd()
+        os.chdir(td)
+        try:
+            import query_inferencer as ref_qi
+            inf = ref_qi.QueryInferencer(str(art), device=torch.device("cpu"))
+            probe = ["machine learning model", "deep neural network layer", "vector search index ?", "zzz qqq"]
+            q_emb = np.stack([inf.get_query_embedding(q) for q in probe])
+        finally:
+            os.chdir(cwd)
+    blob = {"cfg": json.dumps(full), "saved_cfg": json.dumps(saved_cfg), "words": json.dumps(words),
+            "triplets": json.dumps(triplets), "n_val": len(val), "documents": json.dumps(documents),
+            "doc_emb": doc_emb, "tfidf_indptr": mat.indptr, "tfidf_indices": mat.indices, "tfidf_data": mat.data,
+            "tfidf_vocab": json.dumps({k: int(v) for k, v in vocab.items()}), "tfidf_shape": np.array(mat.shape),
+            "state_keys": json.dumps(state_keys), "weight_seeds": np.array([31, 32]),
+            "batch_metrics": json.dumps({k: float(v) for k, v in bm.items()}), "batch_loss": float(bl),
+            "corpus_metrics": json.dumps({k: float(v) for k, v in cm.items()}), "corpus_seed": 1234,
+            "probe_queries": json.dumps(probe), "probe_emb": q_emb}
+    np.savez_compressed(OUT / "artifacts_eval.npz", **blob)
+    print("artifacts/eval ok", bm, cm)
+
+
 def main():
     torch.manual_seed(0)
     torch.set_num_threads(1)          # deterministic reductions
@@ -214,6 +299,7 @@ def main():
     case_cfgdims()
     case_search()
     case_inferencer_hybrid()
+    case_artifacts_eval()
 
 
 if __name__ == "__main__":

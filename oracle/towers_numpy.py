@@ -183,6 +183,63 @@ def hybrid_search_simple(dense_cos_all, tfidf_cos_all, alpha: float, top_k: int 
     return top, combined[top]
 
 
+def frontend_search(query_emb, doc_emb, documents, indptr, indices, data, q_idx, q_val, alpha: float,
+                    n_candidates: int = 50, n_results: int = 10, space: str = "l2"):
+    """The whole `/search` handler — reference `frontend/main.py:102-210` — for one query, with the
+    exact cosine top-50 standing in for `collection.query` (`:153-156`; Chroma is absent here).
+    Returns the list that becomes `results` (without the rank / id decoration of `:206-209`)."""
+    q_idx, q_val = np.asarray(q_idx), np.asarray(q_val, dtype=np.float64)
+    n = len(documents)
+    if alpha == 0.0:                                   # keyword branch, `:119-147`
+        sims = np.array([csr_row_dot(indptr, indices, data, r, q_idx, q_val) for r in range(n)], dtype=np.float64)
+        if n > n_results:
+            top = np.argpartition(sims, -n_results)[-n_results:]
+            top = top[np.argsort(sims[top])[::-1]]
+        else:
+            top = np.argsort(sims)[::-1]
+        return [{"doc": documents[i], "score": float(sims[i]), "dense_score": 0.0, "tfidf_score": float(sims[i])}
+                for i in top if sims[i] > 1e-5]
+    kc = min(n_candidates, n)
+    s, i = cosine_topk(np.asarray(query_emb, np.float32)[None, :], doc_emb, kc, dtype=np.float64)
+    order, fin, sem, tf = hybrid_rerank_frontend(i[0], s[0], indptr, indices, data, q_idx, q_val, alpha,
+                                                 top_n=min(n_results, kc), space=space)
+    return [{"doc": documents[int(i[0][o])], "score": float(f), "dense_score": float(se), "tfidf_score": float(t)}
+            for o, f, se, t in zip(order, fin, sem, tf)]
+
+
+def batch_eval_metrics(query_embs, doc_embs, top_k=(1, 5, 10)) -> dict:
+    """`BatchEvaluator.evaluate` metrics — reference `backend/evaluators.py:49-77`: document i is the
+    positive of query i; rank = position in a descending sort of row i (ties: lower index first)."""
+    sim = np.asarray(query_embs, np.float64) @ np.asarray(doc_embs, np.float64).T
+    n = sim.shape[0]
+    ranks = np.empty(n, dtype=np.int64)
+    for i in range(n):
+        order = np.lexsort((np.arange(sim.shape[1]), -sim[i]))
+        ranks[i] = int(np.nonzero(order == i)[0][0]) + 1
+    out = {f"Recall@{k}": float((ranks <= k).mean()) for k in top_k}
+    out["MRR"] = float((1.0 / ranks).mean())
+    return out, ranks
+
+
+def corpus_eval_metrics(query_embs, doc_embs, queries, query_to_positives, documents, top_k=(1, 5, 10)) -> dict:
+    """`CorpusEvaluator` metrics — reference `backend/evaluators.py:134-209` — from embeddings:
+    Recall@k = found positives / positives present in the candidate pool, Hit@k = any positive found."""
+    doc_set = set(documents)
+    acc = {f"Recall@{k}": [] for k in top_k}
+    acc.update({f"Hit@{k}": [] for k in top_k})
+    _, top = cosine_topk(np.asarray(query_embs, np.float32), np.asarray(doc_embs, np.float32), max(top_k), dtype=np.float64)
+    for qi, q in enumerate(queries):
+        known = query_to_positives[q]
+        avail = [d for d in known if d in doc_set]
+        if not avail:
+            continue
+        for k in top_k:
+            found = len([documents[j] for j in top[qi, :k] if documents[j] in known])
+            acc[f"Recall@{k}"].append(found / len(avail))
+            acc[f"Hit@{k}"].append(1 if found > 0 else 0)
+    return {m: (float(np.mean(v)) if v else 0.0) for m, v in acc.items()}
+
+
 # --------------------------------------------------------------------------- optimiser
 def clip_grad_norm(grads: "list[np.ndarray]", max_norm: float = 1.0):
     """`torch.nn.utils.clip_grad_norm_(params, max_norm)` — reference `backend/main.py:257`:

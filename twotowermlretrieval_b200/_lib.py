@@ -44,6 +44,7 @@ _SIGNATURES = {
     "ttr_score_topk": [P, I32, P, I64, I32, I32, I64, P, P, P, I64, P],
     "ttr_topk_merge": [P, P, I32, I32, I32, I32, P, P, P],
     "ttr_topk_merge_peers": [P, P, P, I32, I32, I32, I32, P, P, P, P],
+    "ttr_positive_rank": [P, P, P, I32, I64, I32, P, P, P],
     "ttr_dropout": [P, I64, F32, ctypes.c_uint64, P, P, P],
     "ttr_blend_topk": [P, F32, P, I64, I32, P, P, P, P, P, I32, F64, I32, P, P, P, P, P],
     "ttr_hybrid_rerank": [P, P, I32, I32, I64, P, P, P, P, P, P, P, F64, I32, I32, P, P, P, P, P],
