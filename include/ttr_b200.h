@@ -51,7 +51,8 @@ int ttr_seq_plan(const int64_t* ids, int B, int T, int32_t* lengths, int32_t* or
 /* ---- K1: embedding gather --------------------------------------------------------------
  * Replaces `self.embedding(x)` (backend/model.py:49).  Writes the packed token matrix
  * X[offsets[s] + t, 0:E] = table[ids[order[s], t], 0:E] for t < length.  `round_tf32` != 0
- * rounds to TF32 (round-to-nearest) because X only feeds the tensor-core projection. */
+ * rounds to TF32 (round-to-nearest) because X only feeds the tensor-core projection; the value 2
+ * makes X an fp16 [Mtok, E] matrix (E % 4 == 0) for the kind::f16 inference pipeline. */
 int ttr_embed_gather(const int64_t* ids, int B, int T, const float* table, int64_t V, int E,
                      const int32_t* order, const int32_t* offsets, float* X, int round_tf32,
                      void* stream);
@@ -64,6 +65,12 @@ int ttr_embed_gather(const int64_t* ids, int B, int T, const float* table, int64
  * Requirements: K % 4 == 0, N % 8 == 0, A/W/C 16-byte aligned. */
 int ttr_gemm_tf32_bias(const float* A, const float* W, const float* bias, float* C,
                        int m_bound, const int32_t* m_valid, int N, int K, void* stream);
+/* Same contraction with fp16 storage: A16 fp16 [m_bound, K], W16 fp16 [N, K] (ttr_f32_to_f16 of W_ih),
+ * bias fp32 [N], C16 fp16 [m_bound, N]; kind::f16 MMAs, fp32 accumulation.  K % 8 == 0, N % 8 == 0. */
+int ttr_gemm_f16_bias(const void* A16, const void* W16, const float* bias, void* C16, int m_bound,
+                      const int32_t* m_valid, int N, int K, void* stream);
+/* dst[i] = fp16(src[i]) (round to nearest even), n elements. */
+int ttr_f32_to_f16(const float* src, void* dst, int64_t n, void* stream);
 /* Same contract, plain fp32 CUDA-core kernel.  Test-only reference for the tcgen05 path. */
 int ttr_debug_gemm_fp32_bias(const float* A, const float* W, const float* bias, float* C,
                              int m_bound, const int32_t* m_valid, int N, int K, void* stream);
@@ -107,6 +114,13 @@ int ttr_gru_recurrence_fwd_ws(const float* gi, const float* w_hh, const float* b
                               const int32_t* order, const int32_t* offsets, int B, int H, int dirs,
                               float* y, float* h_last, float* saved, void* workspace,
                               int64_t workspace_bytes, void* stream);
+/* Inference pipeline in fp16 storage (same 11-bit significand as the tf32 operands; fp32 accumulation,
+ * bias and recurrent state): gi16 fp16 [Mtok, dirs*3H] from ttr_gemm_f16_bias, y16 fp16 [Mtok, dirs*H]
+ * (NULL for the last layer) feeds the next layer's projection.  H == 256 only; needs the workspace. */
+int ttr_gru_recurrence_fwd_f16(const void* gi16, const float* w_hh, const float* b_hh,
+                               const int32_t* order, const int32_t* offsets, int B, int H, int dirs,
+                               void* y16, float* h_last, void* workspace, int64_t workspace_bytes,
+                               void* stream);
 /* BPTT of one layer.  In: dy [Mtok, dirs*H] (grad wrt per-step outputs, NULL = zero),
  * dh_last [B, dirs*H] (grad wrt final states, original row order, NULL = zero), y (this
  * layer's forward outputs), saved.  Out: dgi [Mtok, dirs*3H] (grad wrt gi, also the b_ih
@@ -143,6 +157,9 @@ int ttr_positive_rank(const float* Q, const float* docs, const int64_t* target, 
  * bit9 = select-merge re-reads candidates from L2 instead of staging them in shared memory,
  * bit10 = H=256 GRU forward on the fp32 CUDA-core cluster kernel instead of the tcgen05 one. */
 int ttr_debug_set_flags(int flags);
+int ttr_debug_get_flags(int* out);
+/* Diagnostic: number of 8-CTA clusters of the tcgen05 recurrence the device holds at once. */
+int ttr_debug_gru_tc_max_clusters(int* out);
 /* Diagnostic: device buffer (8 * 256 int64) receiving the pipeline timeline (SM clock at five
  * events per document tile) of CTA (0,0) of the tcgen05 scorer; NULL switches it off. */
 int ttr_debug_set_trace(long long* trace);

@@ -34,6 +34,28 @@ def test_tf32_gemm_matches_fp64(cuda_device, M, N, K):
     assert float((Cf.double() - ref).abs().max()) <= 1e-5 * max(scale, 1.0)
 
 
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (1, 8, 8), (300, 1536, 200), (1000, 1536, 512), (777, 96, 24),
+                                   (129, 104, 40), (4096, 1536, 200)])
+def test_f16_gemm_matches_fp64_of_the_rounded_operands(cuda_device, M, N, K):
+    """kind::f16 variant (fp16 A/W/C storage, fp32 accumulation + bias): exact up to the fp32 accumulation
+    order and the final fp16 rounding when compared on the SAME fp16-rounded operands."""
+    g = torch.Generator(device=cuda_device).manual_seed(M + N + K)
+    A = (torch.randn(M, K, device=cuda_device, generator=g) * 0.4).half()
+    W32 = (torch.rand(N, K, device=cuda_device, generator=g) - 0.5) / 8
+    b = torch.randn(N, device=cuda_device, generator=g) * 0.05
+    W = torch.empty(N, K, dtype=torch.float16, device=cuda_device)
+    _lib.call("ttr_f32_to_f16", W32, W, W32.numel())
+    assert torch.equal(W, W32.half())
+    C = torch.full((M, N), float("nan"), dtype=torch.float16, device=cuda_device)
+    _lib.call("ttr_gemm_f16_bias", A, W, b, C, M, None, N, K)
+    torch.cuda.synchronize()
+    ref = A.double() @ W.double().t() + b.double()
+    scale = float((A.double().abs() @ W.double().abs().t()).max())
+    err = (C.double() - ref).abs()
+    # fp16 result: half an ulp of the value (2^-11 relative) + fp32 accumulation noise
+    assert float((err - ref.abs() * 2.0 ** -11).max()) <= 2e-6 * max(scale, 1.0), float(err.max())
+
+
 def test_dynamic_row_count_leaves_tail_untouched(cuda_device):
     A = torch.randn(1000, 200, device=cuda_device)
     W = torch.randn(1536, 200, device=cuda_device) / 16

@@ -4,7 +4,10 @@ sys.path.insert(0, ".")
 from twotowermlretrieval_b200 import TwoTowerModel, synth, _lib
 from twotowermlretrieval_b200 import towers
 
+import os
 dev = torch.device("cuda:0")
+if os.environ.get("TTR_DEBUG_FLAGS"):
+    _lib.call_nostream("ttr_debug_set_flags", int(os.environ["TTR_DEBUG_FLAGS"]))
 cfg = synth.default_config()
 torch.manual_seed(0)
 model = TwoTowerModel(cfg, None)
@@ -46,9 +49,11 @@ tot = sum(sum(v) for v in agg.values())
 for name, v in sorted(agg.items(), key=lambda kv: -sum(kv[1])):
     print(f"  {name:28s} calls {len(v):3d} total {sum(v):8.2f} ms  ({100*sum(v)/tot:5.1f} %)")
 # projection GEMM utilisation: per layer FLOPs
-g = [e0.elapsed_time(e1) for n, e0, e1 in events if n == "ttr_gemm_tf32_bias"]
+g = [e0.elapsed_time(e1) for n, e0, e1 in events if n in ("ttr_gemm_tf32_bias", "ttr_gemm_f16_bias")]
+kind = "fp16" if any(n == "ttr_gemm_f16_bias" for n, _, _ in events) else "tf32"
+bpe = 2 if kind == "fp16" else 4
 nb = len(batches)
 l0 = sum(g[0::2]); l1 = sum(g[1::2])
 f0 = 2 * toks * 200 * 1536; f1 = 2 * toks * 512 * 1536
-print(f"  input projection L0: {l0:.2f} ms = {f0/l0/1e9:.1f} TFLOP/s ; L1: {l1:.2f} ms = {f1/l1/1e9:.1f} TFLOP/s (tf32; valid tokens only)")
-print(f"  output bytes gi per layer: {toks*1536*4/1e9:.2f} GB -> L0 {toks*1536*4/l0/1e6:.0f} GB/s, L1 {toks*1536*4/l1/1e6:.0f} GB/s write")
+print(f"  input projection L0: {l0:.2f} ms = {f0/l0/1e9:.1f} TFLOP/s ; L1: {l1:.2f} ms = {f1/l1/1e9:.1f} TFLOP/s ({kind}; valid tokens only)")
+print(f"  output bytes gi per layer: {toks*1536*bpe/1e9:.2f} GB -> L0 {toks*1536*bpe/l0/1e6:.0f} GB/s, L1 {toks*1536*bpe/l1/1e6:.0f} GB/s write")

@@ -20,6 +20,8 @@ P, I32, I64, F32, F64 = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_
 _SIGNATURES = {
     "ttr_sm_count": [P],
     "ttr_debug_set_flags": [I32],
+    "ttr_debug_get_flags": [P],
+    "ttr_debug_gru_tc_max_clusters": [P],
     "ttr_debug_set_trace": [P],
     "ttr_seq_plan": [P, I32, I32, P, P, P, P, P],
     "ttr_embed_gather": [P, I32, I32, P, I64, I32, P, P, P, I32, P],
@@ -32,6 +34,9 @@ _SIGNATURES = {
     "ttr_zero_tail_rows": [P, I32, P, I32, P],
     "ttr_gru_recurrence_fwd": [P, P, P, P, P, I32, I32, I32, P, P, P, P],
     "ttr_gru_recurrence_fwd_ws": [P, P, P, P, P, I32, I32, I32, P, P, P, P, I64, P],
+    "ttr_gru_recurrence_fwd_f16": [P, P, P, P, P, I32, I32, I32, P, P, P, I64, P],
+    "ttr_gemm_f16_bias": [P, P, P, P, I32, P, I32, I32, P],
+    "ttr_f32_to_f16": [P, P, I64, P],
     "ttr_gru_recurrence_bwd": [P, P, P, P, P, P, P, I32, I32, I32, P, P, P],
     "ttr_gru_whh_grad": [P, P, P, I32, I32, I32, I32, P, P, I32, P],
     "ttr_proj_l2norm_fwd": [P, P, P, I32, I32, I32, I32, P, P, P],

@@ -8,6 +8,7 @@
 // warps 4-7 = epilogue.  The number of valid rows is read from device memory so the caller
 // never synchronises on the packed token count.
 #include <cudaTypedefs.h>
+#include <cuda_fp16.h>
 
 #include "common.cuh"
 #include "ptx.cuh"
@@ -28,10 +29,16 @@ constexpr int G_OUT_BYTES = GM * 32 * 4;   // staging buffer of one 128 x 32 out
 
 extern int g_debug_flags;
 
+// F16 = true: A, W and C are fp16 (kind::f16 MMAs, 64 halves per 128-byte k-block, fp32 accumulation and
+// bias add, fp16 result) — the encode path's variant.  fp16 and tf32 carry the same 11-bit significand, so
+// the products are as exact as the tf32 ones; what changes is the traffic: operands and the 6 KB/token gi
+// row halve.  Measured with fp32 operands the kernel was bound by the SM's L2 read port on the operand
+// tiles (524 KB per 128x128x512 tile = 59 B/clk/SM) and by the output stores, not by the tensor pipe.
+template <bool F16>
 __global__ void __launch_bounds__(G_THREADS, 1)
-gemm_tf32_bias_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
+gemm_bias_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
                       const __grid_constant__ CUtensorMap map_c, const float* __restrict__ bias, int m_bound,
-                      const int32_t* __restrict__ m_valid, int N, int K) {
+                      const int32_t* __restrict__ m_valid, int N, int K, int dbg) {
   extern __shared__ unsigned char smem_raw[];
   // [stages][A | B]; SWIZZLE_128B atoms need 1024-byte alignment in the shared window
   unsigned char* tiles = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -46,7 +53,8 @@ gemm_tf32_bias_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
   const int M = m_valid ? min(m_bound, *m_valid) : m_bound;
   const int m_tiles = ceil_div(M, GM), n_tiles = ceil_div(N, GN);
   const int total_tiles = m_tiles * n_tiles;
-  const int k_blocks = ceil_div(K, GK);
+  constexpr int GKE = F16 ? 2 * GK : GK;            // elements per 128-byte k-block
+  const int k_blocks = ceil_div(K, GKE);
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < G_STAGES; ++s) { ptx::mbar_init(full_bar + s, 1); ptx::mbar_init(empty_bar + s, 1); }
@@ -78,15 +86,15 @@ gemm_tf32_bias_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
         unsigned char* a_dst = tiles + s * G_STAGE_BYTES;
         if (ptx::elect_one()) {
           ptx::mbar_arrive_expect_tx(full_bar + s, G_STAGE_BYTES);
-          ptx::tma_load_2d(a_dst, &map_a, kb * GK, m0, full_bar + s);
-          ptx::tma_load_2d(a_dst + G_A_BYTES, &map_w, kb * GK, n0, full_bar + s);
+          ptx::tma_load_2d(a_dst, &map_a, kb * GKE, m0, full_bar + s);
+          ptx::tma_load_2d(a_dst + G_A_BYTES, &map_w, kb * GKE, n0, full_bar + s);
         }
         __syncwarp();
       }
     }
   } else if (warp == 1) {
     // ===== MMA issuer (whole warp runs the loop; one elected lane issues) =====
-    constexpr uint32_t idesc = ptx::make_idesc_tf32(GM, GN);
+    constexpr uint32_t idesc = F16 ? ptx::make_idesc_f16(GM, GN) : ptx::make_idesc_tf32(GM, GN);
     int it = 0, local = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
       const int buf = local & 1;
@@ -105,8 +113,9 @@ gemm_tf32_bias_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
         if (ptx::elect_one()) {
 #pragma unroll
           for (int k = 0; k < GK / 8; ++k) {
-            // advance 8 tf32 = 32 bytes inside the 128-byte swizzle row: +2 in 16-byte units
-            ptx::mma_tf32_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+            // advance 8 tf32 / 16 halves = 32 bytes inside the 128-byte swizzle row: +2 in 16-byte units
+            if (F16) ptx::mma_f16_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+            else ptx::mma_tf32_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
           }
           ptx::mma_commit(empty_bar + s);                 // smem slot free once these MMAs retire
           if (kb == k_blocks - 1) ptx::mma_commit(acc_full + buf);   // accumulator complete
@@ -129,12 +138,17 @@ gemm_tf32_bias_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
       const int m0 = (tile / n_tiles) * GM, n0 = (tile % n_tiles) * GN;
       ptx::mbar_wait(acc_full + buf, aph);
       ptx::tc_fence_after_sync();
+      constexpr int CW = F16 ? 64 : 32;                   // columns per 128-byte staging row
 #pragma unroll 1
-      for (int c0 = 0; c0 < GN; c0 += 32, ++chunk_no) {
-        uint32_t r[32];
-        ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * G_ACC_COLS + c0, r);
+      for (int c0 = 0; c0 < GN; c0 += CW, ++chunk_no) {
+        uint32_t r[CW];
+#pragma unroll
+        for (int h = 0; h < CW / 32; ++h) {
+          uint32_t (&rh)[32] = *reinterpret_cast<uint32_t(*)[32]>(r + 32 * h);
+          ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * G_ACC_COLS + c0 + 32 * h, rh);
+        }
         ptx::tmem_ld_wait();
-        if (c0 + 32 >= GN) {                              // last read of this accumulator: hand it back
+        if (c0 + CW >= GN) {                              // last read of this accumulator: hand it back
           ptx::tc_fence_before_sync();
           __syncwarp();
           if (lane == 0) ptx::mbar_arrive(acc_empty + buf);
@@ -143,22 +157,36 @@ gemm_tf32_bias_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
         // the store that used this staging buffer two chunks ago must have finished reading it
         if (warp == 4 && lane == 0) ptx::bulk_wait_group_read<1>();
         ptx::named_bar_sync(1, 128);
-        float4* row = reinterpret_cast<float4*>(stg + r_in_tile * 128);
+        uint4* row = reinterpret_cast<uint4*>(stg + r_in_tile * 128);
+        if (!(dbg & (1 << 18)))                                       // bit 18: (timing experiment) skip bias + staging
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int n = n0 + c0 + 4 * j;
-          float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (bias && n + 3 < N) bv = __ldg(reinterpret_cast<const float4*>(bias + n));
-          float4 o;
-          o.x = __uint_as_float(r[4 * j + 0]) + bv.x;
-          o.y = __uint_as_float(r[4 * j + 1]) + bv.y;
-          o.z = __uint_as_float(r[4 * j + 2]) + bv.z;
-          o.w = __uint_as_float(r[4 * j + 3]) + bv.w;
-          row[j ^ (r_in_tile & 7)] = o;                   // SWIZZLE_128B: 16-byte chunk index XOR (row mod 8)
+        for (int j = 0; j < 8; ++j) {                     // eight 16-byte chunks of the staging row
+          constexpr int EPC = CW / 8;                     // elements per chunk: 4 floats or 8 halves
+          const int n = n0 + c0 + EPC * j;
+          float o[EPC];
+#pragma unroll
+          for (int e = 0; e < EPC; e += 4) {
+            float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (bias && n + e + 3 < N) bv = __ldg(reinterpret_cast<const float4*>(bias + n + e));
+            o[e + 0] = __uint_as_float(r[EPC * j + e + 0]) + bv.x;
+            o[e + 1] = __uint_as_float(r[EPC * j + e + 1]) + bv.y;
+            o[e + 2] = __uint_as_float(r[EPC * j + e + 2]) + bv.z;
+            o[e + 3] = __uint_as_float(r[EPC * j + e + 3]) + bv.w;
+          }
+          uint4 pk;
+          if (F16) {
+            const __half2 h0 = __floats2half2_rn(o[0], o[1]), h1 = __floats2half2_rn(o[2], o[3]);
+            const __half2 h2 = __floats2half2_rn(o[EPC - 4], o[EPC - 3]), h3 = __floats2half2_rn(o[EPC - 2], o[EPC - 1]);
+            pk = make_uint4(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1),
+                            *reinterpret_cast<const uint32_t*>(&h2), *reinterpret_cast<const uint32_t*>(&h3));
+          } else {
+            pk = make_uint4(__float_as_uint(o[0]), __float_as_uint(o[1]), __float_as_uint(o[2]), __float_as_uint(o[3]));
+          }
+          row[j ^ (r_in_tile & 7)] = pk;                  // SWIZZLE_128B: 16-byte chunk index XOR (row mod 8)
         }
         ptx::fence_proxy_async_smem();
         ptx::named_bar_sync(1, 128);
-        if (warp == 4 && lane == 0) {
+        if (warp == 4 && lane == 0 && !(dbg & 2048)) {          // bit 11: timing experiment without the stores
           ptx::tma_store_2d(&map_c, stg, n0 + c0, m0);
           ptx::bulk_commit_group();
         }
@@ -218,7 +246,48 @@ int make_pitched_map(CUtensorMap* map, const float* base, int64_t rows, int64_t 
   return TTR_OK;
 }
 
+// row-major fp16 [rows, cols] matrix, box = [box_rows, 64 halves], SWIZZLE_128B, OOB -> 0
+int make_f16_rowmajor_map(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int box_rows) {
+  auto enc = get_encode_fn();
+  TTR_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
+  cuuint32_t box[2] = {64u, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1u, 1u};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  TTR_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (fp16) failed with CUresult %d (rows=%lld cols=%lld)", (int)r,
+              (long long)rows, (long long)cols);
+  return TTR_OK;
+}
+
 }  // namespace ttr
+
+extern "C" int ttr_gemm_f16_bias(const void* A16, const void* W16, const float* bias, void* C16, int m_bound,
+                                 const int32_t* m_valid, int N, int K, void* stream) {
+  using namespace ttr;
+  TTR_REQUIRE(m_bound >= 1 && N >= 1 && K >= 1, "ttr_gemm_f16_bias: bad shape");
+  TTR_REQUIRE(K % 8 == 0 && N % 8 == 0, "ttr_gemm_f16_bias: K=%d and N=%d must be multiples of 8", K, N);
+  TTR_REQUIRE(((uintptr_t)A16 & 15) == 0 && ((uintptr_t)W16 & 15) == 0 && ((uintptr_t)C16 & 15) == 0 &&
+                  ((uintptr_t)bias & 15) == 0,
+              "ttr_gemm_f16_bias: operands must be 16-byte aligned");
+  CUtensorMap map_a, map_w, map_c;
+  int rc = make_f16_rowmajor_map(&map_a, A16, m_bound, K, GM);
+  if (rc != TTR_OK) return rc;
+  rc = make_f16_rowmajor_map(&map_w, W16, N, K, GN);
+  if (rc != TTR_OK) return rc;
+  rc = make_f16_rowmajor_map(&map_c, C16, m_bound, N, GM);
+  if (rc != TTR_OK) return rc;
+  const size_t smem = (size_t)G_STAGES * G_STAGE_BYTES + 2 * G_OUT_BYTES + (2 * G_STAGES + 4) * sizeof(uint64_t) + 16 + 1024;
+  TTR_CHECK_CUDA(cudaFuncSetAttribute(gemm_bias_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int tiles = ceil_div(m_bound, GM) * ceil_div(N, GN);
+  const int grid = std::min(tiles, sm_count());
+  gemm_bias_kernel<true><<<grid, G_THREADS, smem, (cudaStream_t)stream>>>(map_a, map_w, map_c, bias, m_bound, m_valid, N, K,
+                                                                         g_debug_flags);
+  TTR_CHECK_LAUNCH();
+  return TTR_OK;
+}
 
 extern "C" int ttr_gemm_tf32_bias(const float* A, const float* W, const float* bias, float* C, int m_bound,
                                   const int32_t* m_valid, int N, int K, void* stream) {
@@ -236,10 +305,11 @@ extern "C" int ttr_gemm_tf32_bias(const float* A, const float* W, const float* b
   rc = make_rowmajor_map(&map_c, C, m_bound, N, GM, false);
   if (rc != TTR_OK) return rc;
   const size_t smem = (size_t)G_STAGES * G_STAGE_BYTES + 2 * G_OUT_BYTES + (2 * G_STAGES + 4) * sizeof(uint64_t) + 16 + 1024;
-  TTR_CHECK_CUDA(cudaFuncSetAttribute(gemm_tf32_bias_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  TTR_CHECK_CUDA(cudaFuncSetAttribute(gemm_bias_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int tiles = ceil_div(m_bound, GM) * ceil_div(N, GN);
   const int grid = std::min(tiles, sm_count());
-  gemm_tf32_bias_kernel<<<grid, G_THREADS, smem, (cudaStream_t)stream>>>(map_a, map_w, map_c, bias, m_bound, m_valid, N, K);
+  gemm_bias_kernel<false><<<grid, G_THREADS, smem, (cudaStream_t)stream>>>(map_a, map_w, map_c, bias, m_bound, m_valid, N, K,
+                                                                          g_debug_flags);
   TTR_CHECK_LAUNCH();
   return TTR_OK;
 }

@@ -266,7 +266,7 @@ gru_fwd_generic_kernel(GruFwdArgs a, int H) {
 
 int launch_gru_fwd_tc(const float* gi, const float* w_hh, const float* b_hh, const int32_t* order,
                       const int32_t* offsets, int B, int dirs, float* y, float* h_last, float* saved, void* workspace,
-                      cudaStream_t st);
+                      bool half_io, cudaStream_t st);
 int64_t gru_fwd_tc_workspace_bytes(int B, int dirs);
 
 }  // namespace ttr
@@ -278,7 +278,7 @@ extern "C" int ttr_debug_set_flags(int flags) {
 
 static int gru_recurrence_fwd_impl(const float* gi, const float* w_hh, const float* b_hh, const int32_t* order,
                                   const int32_t* offsets, int B, int H, int dirs, float* y, float* h_last,
-                                  float* saved, void* workspace, int64_t workspace_bytes, void* stream) {
+                                  float* saved, void* workspace, int64_t workspace_bytes, bool half_io, void* stream) {
   using namespace ttr;
   TTR_REQUIRE(B >= 1 && H >= 1 && (dirs == 1 || dirs == 2), "ttr_gru_recurrence_fwd: bad shape");
   TTR_REQUIRE(h_last != nullptr, "ttr_gru_recurrence_fwd: h_last is required");
@@ -288,8 +288,11 @@ static int gru_recurrence_fwd_impl(const float* gi, const float* w_hh, const flo
     // default for H = 256: recurrent product on the tensor cores (gru_fwd_tc.cu)
     TTR_REQUIRE(workspace_bytes >= gru_fwd_tc_workspace_bytes(B, dirs), "ttr_gru_recurrence_fwd_ws: workspace of %lld B < %lld B",
                 (long long)workspace_bytes, (long long)gru_fwd_tc_workspace_bytes(B, dirs));
-    return launch_gru_fwd_tc(gi, w_hh, b_hh, order, offsets, B, dirs, y, h_last, saved, workspace, st);
-  } else if (H == GH && !(g_debug_flags & 1)) {
+    return launch_gru_fwd_tc(gi, w_hh, b_hh, order, offsets, B, dirs, y, h_last, saved, workspace, half_io, st);
+  }
+  TTR_REQUIRE(!half_io, "ttr_gru_recurrence_fwd_f16: only the tcgen05 H = 256 kernel reads fp16 gi (H=%d, flags=%d)", H,
+              g_debug_flags);
+  if (H == GH && !(g_debug_flags & 1)) {
     // no workspace (or debug bit 10): the fp32 CUDA-core cluster kernel (W_hh in registers, warp-shuffle reductions)
     const size_t smem = (size_t)2 * GCL * GCS * sizeof(float) + 3 * GBT * sizeof(int);
     TTR_CHECK_CUDA(cudaFuncSetAttribute(gru_fwd_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -311,7 +314,7 @@ static int gru_recurrence_fwd_impl(const float* gi, const float* w_hh, const flo
 extern "C" int ttr_gru_recurrence_fwd(const float* gi, const float* w_hh, const float* b_hh,
                                       const int32_t* order, const int32_t* offsets, int B, int H, int dirs,
                                       float* y, float* h_last, float* saved, void* stream) {
-  return gru_recurrence_fwd_impl(gi, w_hh, b_hh, order, offsets, B, H, dirs, y, h_last, saved, nullptr, 0, stream);
+  return gru_recurrence_fwd_impl(gi, w_hh, b_hh, order, offsets, B, H, dirs, y, h_last, saved, nullptr, 0, false, stream);
 }
 
 extern "C" int64_t ttr_gru_fwd_workspace_bytes(int B, int H, int dirs) {
@@ -323,5 +326,19 @@ extern "C" int ttr_gru_recurrence_fwd_ws(const float* gi, const float* w_hh, con
                                          float* y, float* h_last, float* saved, void* workspace,
                                          int64_t workspace_bytes, void* stream) {
   return gru_recurrence_fwd_impl(gi, w_hh, b_hh, order, offsets, B, H, dirs, y, h_last, saved, workspace,
-                                 workspace_bytes, stream);
+                                 workspace_bytes, false, stream);
+}
+
+extern "C" int ttr_gru_recurrence_fwd_f16(const void* gi16, const float* w_hh, const float* b_hh,
+                                          const int32_t* order, const int32_t* offsets, int B, int H, int dirs,
+                                          void* y16, float* h_last, void* workspace, int64_t workspace_bytes,
+                                          void* stream) {
+  TTR_REQUIRE(workspace != nullptr, "ttr_gru_recurrence_fwd_f16: workspace is required");
+  return gru_recurrence_fwd_impl(reinterpret_cast<const float*>(gi16), w_hh, b_hh, order, offsets, B, H, dirs,
+                                 reinterpret_cast<float*>(y16), h_last, nullptr, workspace, workspace_bytes, true, stream);
+}
+
+extern "C" int ttr_debug_get_flags(int* out) {
+  *out = ttr::g_debug_flags;
+  return TTR_OK;
 }

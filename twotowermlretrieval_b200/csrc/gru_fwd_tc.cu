@@ -65,13 +65,13 @@ constexpr int TC_TMEM_COLS = TC_ACC_COLS * TC_CHAINS;
 constexpr int TC_SMEM = TC_CHAINS * TC_A_BYTES + TC_B_BYTES + TC_NG * 4 + 3 * TC_TILE * 4 + TC_CHAINS * 3 * 8 + 8;
 
 struct GruTcArgs {
-  const float* gi;
+  const float* gi;          // HALF_IO: const __half*
   const float* w_hh;
   const float* b_hh;
   const int32_t* order;
   const int32_t* offsets;
   int B, dirs;
-  float* y;
+  float* y;                 // HALF_IO: __half*
   float* h_last;
   float* saved;
   unsigned char* scratch;   // [clusters][chains][2][TC_A_BYTES] operand images for the multicast exchange
@@ -110,15 +110,6 @@ __device__ __forceinline__ void mma_commit_multicast(uint64_t* bar, uint16_t mas
       "h"(mask)
       : "memory");
 }
-__device__ __forceinline__ void mma_f16_ss(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
-                                           uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
-      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
 __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
@@ -145,11 +136,6 @@ __device__ __forceinline__ uint64_t make_kmajor_nosw_desc(uint32_t smem_addr, ui
   d |= (uint64_t)1 << 46;      // descriptor version (Blackwell); layout type 0 = no swizzle
   return d;
 }
-// kind::f16 instruction descriptor: fp16 A and B (format 0), fp32 accumulate, both K-major, dense
-__host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) {
-  return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-}
-
 // 8 fp32 values -> 8 fp16 (round to nearest even) in one 16-byte row of an operand
 __device__ __forceinline__ uint4 pack8(const float* x) {
   uint32_t h[4];
@@ -207,7 +193,9 @@ __device__ __forceinline__ void tanh2(float a, float b, float& ta, float& tb) {
   tb = (1.0f - eb) * da * inv;
 }
 
-// per-step outputs y[tok, col0 + 16 units] of a warp's 32 rows, written row-contiguous (see transpose4)
+// per-step outputs y[tok, col0 + 16 units] of a warp's 32 rows, written row-contiguous (see transpose4);
+// HALF: y holds fp16 (it only feeds the next layer's kind::f16 projection)
+template <bool HALF>
 __device__ __forceinline__ void store_y(float* y, const float (&h)[16], const int (&tok_k)[4], int t,
                                         const int* lens4, int y_ld, int col0, int lane) {
   if (y == nullptr) return;
@@ -216,12 +204,22 @@ __device__ __forceinline__ void store_y(float* y, const float (&h)[16], const in
   for (int k = 0; k < 4; ++k) v[k] = make_float4(h[4 * k], h[4 * k + 1], h[4 * k + 2], h[4 * k + 3]);
   transpose4(v, lane);                         // lane (G, c) now holds units 4c..4c+3 of rows 4G + k
 #pragma unroll
-  for (int k = 0; k < 4; ++k)
-    if (t < lens4[k]) *(reinterpret_cast<float4*>(y + (size_t)tok_k[k] * y_ld + col0) + (lane & 3)) = v[k];
+  for (int k = 0; k < 4; ++k) {
+    if (t >= lens4[k]) continue;
+    if (HALF) {
+      const __half2 lo = __floats2half2_rn(v[k].x, v[k].y), hi = __floats2half2_rn(v[k].z, v[k].w);
+      *(reinterpret_cast<uint2*>(reinterpret_cast<__half*>(y) + (size_t)tok_k[k] * y_ld + col0) + (lane & 3)) =
+          make_uint2(*reinterpret_cast<const uint32_t*>(&lo), *reinterpret_cast<const uint32_t*>(&hi));
+    } else {
+      *(reinterpret_cast<float4*>(y + (size_t)tok_k[k] * y_ld + col0) + (lane & 3)) = v[k];
+    }
+  }
 }
 
 }  // namespace
 
+// HALF_IO: gi is read and y written as fp16 (the inference pipeline; `saved` must then be NULL)
+template <bool HALF_IO>
 __global__ void __cluster_dims__(TC_CL, 1, 1) __launch_bounds__(TC_THREADS, 1)
 gru_fwd_tc_kernel(GruTcArgs a) {
   extern __shared__ __align__(128) unsigned char sm[];
@@ -306,7 +304,8 @@ gru_fwd_tc_kernel(GruTcArgs a) {
   const int tbase = toff[ch * TC_ROWS + row];
   const int maxlen = lens[ch * TC_ROWS];
   const int gi_ld = a.dirs * G3, y_ld = a.dirs * TC_H;
-  const float* gi_base = a.gi + dir * G3 + j0;
+  const float* gi_base = a.gi + dir * G3 + j0;                                   // fp32 view
+  const __half* gi16_base = reinterpret_cast<const __half*>(a.gi) + dir * G3 + j0;   // fp16 view
   float h[16];
 #pragma unroll
   for (int i = 0; i < 16; ++i) h[i] = 0.f;
@@ -314,7 +313,7 @@ gru_fwd_tc_kernel(GruTcArgs a) {
   const uint32_t h_u32 = ptx::smem_u32(h_sm);
   unsigned char* scr = a.scratch + ((size_t)(blockIdx.y * (gridDim.x / TC_CL) + tile) * TC_CHAINS + ch) * 2 * TC_A_BYTES;
   const uint32_t w_u32 = ptx::smem_u32(w_sm);
-  constexpr uint32_t idesc = make_idesc_f16(TC_ROWS, TC_NG);
+  constexpr uint32_t idesc = ptx::make_idesc_f16(TC_ROWS, TC_NG);
   const int kc0 = 4 * rank + 2 * uh;                // k-chunk of this thread's first 8 units
 
   for (int t = 0; t < maxlen; ++t) {
@@ -333,7 +332,7 @@ gru_fwd_tc_kernel(GruTcArgs a) {
         const uint64_t b_desc = make_kmajor_nosw_desc(w_u32, TC_B_LBO, 128);
 #pragma unroll
         for (int ks = 0; ks < TC_H / 16; ++ks)
-          mma_f16_ss(tmem_acc, a_desc + (uint64_t)(ks * (2 * TC_A_LBO >> 4)), b_desc + (uint64_t)(ks * (2 * TC_B_LBO >> 4)),
+          ptx::mma_f16_ss(tmem_acc, a_desc + (uint64_t)(ks * (2 * TC_A_LBO >> 4)), b_desc + (uint64_t)(ks * (2 * TC_B_LBO >> 4)),
                      idesc, ks != 0);
         ptx::mma_commit(mma_done);
         // nobody waits for the last step's signal, and a peer may have left by the time it would land
@@ -354,8 +353,16 @@ gru_fwd_tc_kernel(GruTcArgs a) {
 #pragma unroll
     for (int g = 0; g < 3; ++g)
 #pragma unroll
-      for (int k = 0; k < 4; ++k)
-        g4[g][k] = __ldg(reinterpret_cast<const float4*>(gi_base + (size_t)tok_k[k] * gi_ld + g * TC_H) + c4);
+      for (int k = 0; k < 4; ++k) {
+        if (HALF_IO) {
+          const uint2 raw = __ldg(reinterpret_cast<const uint2*>(gi16_base + (size_t)tok_k[k] * gi_ld + g * TC_H) + c4);
+          const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(&raw.x));
+          const float2 hi = __half22float2(*reinterpret_cast<const __half2*>(&raw.y));
+          g4[g][k] = make_float4(lo.x, lo.y, hi.x, hi.y);
+        } else {
+          g4[g][k] = __ldg(reinterpret_cast<const float4*>(gi_base + (size_t)tok_k[k] * gi_ld + g * TC_H) + c4);
+        }
+      }
 
     ptx::mbar_wait(mma_done, par);
     ptx::tc_fence_after_sync();
@@ -413,7 +420,7 @@ gru_fwd_tc_kernel(GruTcArgs a) {
     if (wg == 0 && lane == 0 && ch == 0) TC_TRACE(5);
     // the exchange is issued first (below, by one thread of warp 0); the per-step outputs leave after the
     // fence so that it only waits for the 32 bytes of scratch per thread, not for the HBM writes
-    if (wg != 0) store_y(a.y, h, tok_k, t, lens + ch * TC_ROWS + q * 32 + grp4, y_ld, dir * TC_H + j0, lane);
+    if (wg != 0) store_y<HALF_IO>(a.y, h, tok_k, t, lens + ch * TC_ROWS + q * 32 + grp4, y_ld, dir * TC_H + j0, lane);
     if (active && wg != 0) {
       if (t == len - 1) {
         float4* hp = reinterpret_cast<float4*>(a.h_last + (size_t)rowid[ch * TC_ROWS + row] * y_ld + dir * TC_H + j0);
@@ -435,7 +442,7 @@ gru_fwd_tc_kernel(GruTcArgs a) {
       }
       __syncwarp();
     }
-    if (wg == 0) store_y(a.y, h, tok_k, t, lens + ch * TC_ROWS + q * 32 + grp4, y_ld, dir * TC_H + j0, lane);
+    if (wg == 0) store_y<HALF_IO>(a.y, h, tok_k, t, lens + ch * TC_ROWS + q * 32 + grp4, y_ld, dir * TC_H + j0, lane);
     if (active && wg == 0) {
       if (t == len - 1) {
         float4* hp = reinterpret_cast<float4*>(a.h_last + (size_t)rowid[ch * TC_ROWS + row] * y_ld + dir * TC_H + j0);
@@ -457,12 +464,19 @@ int64_t gru_fwd_tc_workspace_bytes(int B, int dirs) {
 
 int launch_gru_fwd_tc(const float* gi, const float* w_hh, const float* b_hh, const int32_t* order,
                       const int32_t* offsets, int B, int dirs, float* y, float* h_last, float* saved, void* workspace,
-                      cudaStream_t st) {
+                      bool half_io, cudaStream_t st) {
   GruTcArgs a{gi, w_hh, b_hh, order, offsets, B, dirs, y, h_last, saved, reinterpret_cast<unsigned char*>(workspace),
               g_score_trace};
-  TTR_CHECK_CUDA(cudaFuncSetAttribute(gru_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
   dim3 grid(ceil_div(B, TC_TILE) * TC_CL, dirs);
-  gru_fwd_tc_kernel<<<grid, TC_THREADS, TC_SMEM, st>>>(a);
+  if (half_io) {
+    TTR_REQUIRE(saved == nullptr, "tcgen05 GRU with fp16 gi/y is inference-only (saved must be NULL)");
+    TTR_CHECK_CUDA(cudaFuncSetAttribute(gru_fwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
+    gru_fwd_tc_kernel<true><<<grid, TC_THREADS, TC_SMEM, st>>>(a);
+    TTR_CHECK_LAUNCH();
+    return TTR_OK;
+  }
+  TTR_CHECK_CUDA(cudaFuncSetAttribute(gru_fwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
+  gru_fwd_tc_kernel<false><<<grid, TC_THREADS, TC_SMEM, st>>>(a);
   TTR_CHECK_LAUNCH();
   return TTR_OK;
 }
@@ -472,7 +486,7 @@ int launch_gru_fwd_tc(const float* gi, const float* w_hh, const float* b_hh, con
 // diagnostic: how many 8-CTA clusters of the tcgen05 recurrence the device can hold at once
 extern "C" int ttr_debug_gru_tc_max_clusters(int* out) {
   using namespace ttr;
-  TTR_CHECK_CUDA(cudaFuncSetAttribute(gru_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
+  TTR_CHECK_CUDA(cudaFuncSetAttribute(gru_fwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(TC_CL * 64, 1, 1);
   cfg.blockDim = dim3(TC_THREADS, 1, 1);
@@ -481,6 +495,6 @@ extern "C" int ttr_debug_gru_tc_max_clusters(int* out) {
   attr.id = cudaLaunchAttributeClusterDimension;
   attr.val.clusterDim.x = TC_CL; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
   cfg.attrs = &attr; cfg.numAttrs = 1;
-  TTR_CHECK_CUDA(cudaOccupancyMaxActiveClusters(out, gru_fwd_tc_kernel, &cfg));
+  TTR_CHECK_CUDA(cudaOccupancyMaxActiveClusters(out, gru_fwd_tc_kernel<false>, &cfg));
   return TTR_OK;
 }

@@ -127,6 +127,16 @@ __device__ __forceinline__ void mma_tf32_ss(uint32_t tmem_d, uint64_t desc_a, ui
       "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// D[tmem] (+)= A[smem desc] * B[smem desc], fp16 inputs (K = 16 per instruction), fp32 accumulate
+__device__ __forceinline__ void mma_f16_ss(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                           uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // same with the A operand read from tensor memory (lane = row, one 32-bit column per k element)
 __device__ __forceinline__ void mma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
                                             uint32_t accumulate) {
@@ -193,6 +203,11 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
          | (2u << 10)                  // b_format = TF32
          | ((uint32_t)(N >> 3) << 17)  // n_dim
          | ((uint32_t)(M >> 4) << 24); // m_dim
+}
+
+// kind::f16 instruction descriptor: fp16 A and B (format 0), fp32 accumulate, both K-major, dense
+__host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) {
+  return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
 }  // namespace ptx

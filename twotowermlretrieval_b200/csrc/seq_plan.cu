@@ -6,6 +6,8 @@
 // sorted position s holds row order[s]; its tokens occupy rows offsets[s] .. offsets[s+1]
 // of every per-token matrix (X, gi, y, ...).  Lengths are non-increasing in s so a tile of
 // consecutive positions has similar lengths and the active rows at step t are a prefix.
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace ttr {
@@ -88,6 +90,17 @@ __global__ void __launch_bounds__(128) gather_kernel(const int64_t* __restrict__
     int64_t id = idrow[t];
     if (id < 0 || id >= V) id = 0;   // torch would raise; keep memory-safe
     const float* src = table + id * E;
+    if (round == 2) {
+      // fp16 rows for the kind::f16 projection (E % 4 == 0): 8-byte stores of 4 halves
+      uint2* d2 = reinterpret_cast<uint2*>(reinterpret_cast<__half*>(X) + (int64_t)(off + t) * E);
+      const float4* s4 = reinterpret_cast<const float4*>(src);
+      for (int c = lane; c < E4; c += 32) {
+        const float4 v = __ldg(s4 + c);
+        const __half2 lo = __floats2half2_rn(v.x, v.y), hi = __floats2half2_rn(v.z, v.w);
+        d2[c] = make_uint2(*reinterpret_cast<const uint32_t*>(&lo), *reinterpret_cast<const uint32_t*>(&hi));
+      }
+      continue;
+    }
     float* dst = X + (int64_t)(off + t) * E;
     if ((E & 3) == 0) {
       const float4* s4 = reinterpret_cast<const float4*>(src);
@@ -156,11 +169,33 @@ extern "C" int ttr_seq_plan(const int64_t* ids, int B, int T, int32_t* lengths, 
   return TTR_OK;
 }
 
+namespace ttr {
+__global__ void f32_to_f16_kernel(const float* __restrict__ src, __half* __restrict__ dst, int64_t n) {
+  const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 2;
+  if (i + 1 < n) {
+    const float2 v = *reinterpret_cast<const float2*>(src + i);
+    *reinterpret_cast<__half2*>(dst + i) = __floats2half2_rn(v.x, v.y);
+  } else if (i < n) {
+    dst[i] = __float2half_rn(src[i]);
+  }
+}
+}  // namespace ttr
+
+extern "C" int ttr_f32_to_f16(const float* src, void* dst, int64_t n, void* stream) {
+  using namespace ttr;
+  TTR_REQUIRE(n >= 1 && ((uintptr_t)src & 7) == 0 && ((uintptr_t)dst & 3) == 0, "ttr_f32_to_f16: bad arguments");
+  const int64_t pairs = (n + 1) / 2;
+  f32_to_f16_kernel<<<(unsigned)((pairs + 255) / 256), 256, 0, (cudaStream_t)stream>>>(src, reinterpret_cast<__half*>(dst), n);
+  TTR_CHECK_LAUNCH();
+  return TTR_OK;
+}
+
 extern "C" int ttr_embed_gather(const int64_t* ids, int B, int T, const float* table, int64_t V, int E,
                                 const int32_t* order, const int32_t* offsets, float* X, int round_tf32,
                                 void* stream) {
   using namespace ttr;
   TTR_REQUIRE(B > 0 && T > 0 && E > 0, "ttr_embed_gather: bad shape");
+  TTR_REQUIRE(round_tf32 != 2 || (E & 3) == 0, "ttr_embed_gather: fp16 output needs E %% 4 == 0 (E=%d)", E);
   gather_kernel<<<B, 128, 0, (cudaStream_t)stream>>>(ids, T, table, V, E, order, offsets, X, round_tf32);
   TTR_CHECK_LAUNCH();
   return TTR_OK;

@@ -22,6 +22,18 @@ from . import _lib
 from .model import _ZERO_LEN_MSG
 
 
+def _fp16_pipeline_allowed() -> bool:
+    """Inference runs gather -> projection -> recurrence with fp16 STORAGE of X, gi and the inter-layer y
+    (fp32 accumulation, bias, state) unless TTR_FP32_PIPELINE=1, the fp32 debug GEMM, or a debug flag that
+    forces one of the fp32-only recurrence kernels asks otherwise."""
+    import ctypes
+    if os.environ.get("TTR_FP32_PIPELINE", "0") == "1" or _use_debug_gemm():
+        return False
+    flags = ctypes.c_int(0)
+    _lib.call_nostream("ttr_debug_get_flags", ctypes.byref(flags))
+    return (flags.value & (1 | 2 | 1024)) == 0
+
+
 def _use_debug_gemm() -> bool:
     # test-only switch: route the input projection through the fp32 CUDA-core reference kernel
     return os.environ.get("TTR_DEBUG_FP32_GEMM", "0") == "1"
@@ -56,6 +68,31 @@ class SeqPlan:
             raise RuntimeError(_ZERO_LEN_MSG)
 
 
+def _forward_layers_f16(enc, ids, plan, B, T, H, E, dirs, table, dev) -> torch.Tensor:
+    """The inference pipeline with fp16 storage between the kernels (no autograd, no dropout):
+    gather -> fp16 X; per layer kind::f16 projection -> fp16 gi; tcgen05 recurrence -> fp16 y / fp32 h_last."""
+    Mb = plan.m_bound
+    X = torch.empty(Mb, E, dtype=torch.float16, device=dev)
+    _lib.call("ttr_embed_gather", ids, B, T, table.detach(), table.shape[0], E, plan.order, plan.offsets, X, 2)
+    ws_bytes = int(_lib.load().ttr_gru_fwd_workspace_bytes(B, H, dirs))
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    layer_in, h_last = X, None
+    for layer in range(enc.num_layers):
+        W_ih, b_ih, W_hh, b_hh = enc.layer_weights(layer)
+        W16 = torch.empty(W_ih.shape, dtype=torch.float16, device=dev)
+        _lib.call("ttr_f32_to_f16", W_ih.detach().contiguous(), W16, W_ih.numel())
+        gi = torch.empty(Mb, dirs * 3 * H, dtype=torch.float16, device=dev)
+        _lib.call("ttr_gemm_f16_bias", layer_in, W16, b_ih.detach(), gi, Mb, plan.total, dirs * 3 * H, layer_in.shape[1])
+        last = layer == enc.num_layers - 1
+        y = None if last else torch.empty(Mb, dirs * H, dtype=torch.float16, device=dev)
+        h_last = torch.empty(B, dirs * H, dtype=torch.float32, device=dev)
+        _lib.call("ttr_gru_recurrence_fwd_f16", gi, W_hh.detach(), b_hh.detach(), plan.order, plan.offsets, B, H, dirs,
+                  y, h_last, ws, ws_bytes)
+        del gi
+        layer_in = y
+    return h_last
+
+
 def _forward_impl(enc, ids: torch.Tensor, need_grad: bool, training: bool):
     """Runs the kernels; returns (out, ctx dict for backward or None)."""
     if ids.dim() != 2:
@@ -81,44 +118,49 @@ def _forward_impl(enc, ids: torch.Tensor, need_grad: bool, training: bool):
         plan.check_lengths()
     Mb = plan.m_bound
     tf32 = not _use_debug_gemm()
-    X = torch.empty(Mb, E, dtype=torch.float32, device=dev)
-    _lib.call("ttr_embed_gather", ids, B, T, table.detach(), table.shape[0], E, plan.order, plan.offsets, X,
-              1 if tf32 else 0)
+    no_dropout = not training or enc.rnn.dropout == 0.0 or enc.num_layers == 1
+    if not need_grad and no_dropout and H == 256 and E % 8 == 0 and _fp16_pipeline_allowed():
+        h_last = _forward_layers_f16(enc, ids, plan, B, T, H, E, dirs, table, dev)
+        layer_ins = ys = saveds = masks = None
+    else:
+        X = torch.empty(Mb, E, dtype=torch.float32, device=dev)
+        _lib.call("ttr_embed_gather", ids, B, T, table.detach(), table.shape[0], E, plan.order, plan.offsets, X,
+                  1 if tf32 else 0)
 
-    p_drop = enc.rnn.dropout if training else 0.0
-    layer_in = X
-    layer_ins: List[torch.Tensor] = []      # GEMM input of each layer (X, then dropped outputs)
-    ys: List[Optional[torch.Tensor]] = []   # un-dropped per-step outputs of each layer
-    saveds: List[Optional[torch.Tensor]] = []
-    masks: List[Optional[torch.Tensor]] = []
-    h_last = None
-    for layer in range(enc.num_layers):
-        W_ih, b_ih, W_hh, b_hh = enc.layer_weights(layer)
-        layer_ins.append(layer_in)
-        gi = torch.empty(Mb, dirs * 3 * H, dtype=torch.float32, device=dev)
-        input_projection(layer_in, W_ih, b_ih, gi, Mb, plan.total)
-        last = layer == enc.num_layers - 1
-        y = torch.empty(Mb, dirs * H, dtype=torch.float32, device=dev) if (not last or need_grad) else None
-        saved = torch.empty(Mb, dirs, 4, H, dtype=torch.float32, device=dev) if need_grad else None
-        h_last = torch.empty(B, dirs * H, dtype=torch.float32, device=dev)
-        ws_bytes = int(_lib.load().ttr_gru_fwd_workspace_bytes(B, H, dirs))
-        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev) if ws_bytes else None
-        _lib.call("ttr_gru_recurrence_fwd_ws", gi, W_hh, b_hh, plan.order, plan.offsets, B, H, dirs, y, h_last, saved,
-                  ws, ws_bytes)
-        del gi
-        ys.append(y)
-        saveds.append(saved)
-        mask = None
-        if not last:
-            layer_in = y
-            if p_drop > 0.0:
-                # inter-layer dropout of nn.GRU (model.py:35): scaled keep mask on layer outputs
-                # (seed drawn from torch's CPU generator so torch.manual_seed controls it)
-                seed = int(torch.randint(0, 2 ** 62, (1,)).item())
-                mask = torch.empty_like(y)
-                layer_in = torch.empty_like(y)
-                _lib.call("ttr_dropout", y, y.numel(), float(p_drop), seed, layer_in, mask)
-        masks.append(mask)
+        p_drop = enc.rnn.dropout if training else 0.0
+        layer_in = X
+        layer_ins: List[torch.Tensor] = []      # GEMM input of each layer (X, then dropped outputs)
+        ys: List[Optional[torch.Tensor]] = []   # un-dropped per-step outputs of each layer
+        saveds: List[Optional[torch.Tensor]] = []
+        masks: List[Optional[torch.Tensor]] = []
+        h_last = None
+        for layer in range(enc.num_layers):
+            W_ih, b_ih, W_hh, b_hh = enc.layer_weights(layer)
+            layer_ins.append(layer_in)
+            gi = torch.empty(Mb, dirs * 3 * H, dtype=torch.float32, device=dev)
+            input_projection(layer_in, W_ih, b_ih, gi, Mb, plan.total)
+            last = layer == enc.num_layers - 1
+            y = torch.empty(Mb, dirs * H, dtype=torch.float32, device=dev) if (not last or need_grad) else None
+            saved = torch.empty(Mb, dirs, 4, H, dtype=torch.float32, device=dev) if need_grad else None
+            h_last = torch.empty(B, dirs * H, dtype=torch.float32, device=dev)
+            ws_bytes = int(_lib.load().ttr_gru_fwd_workspace_bytes(B, H, dirs))
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev) if ws_bytes else None
+            _lib.call("ttr_gru_recurrence_fwd_ws", gi, W_hh, b_hh, plan.order, plan.offsets, B, H, dirs, y, h_last,
+                      saved, ws, ws_bytes)
+            del gi
+            ys.append(y)
+            saveds.append(saved)
+            mask = None
+            if not last:
+                layer_in = y
+                if p_drop > 0.0:
+                    # inter-layer dropout of nn.GRU (model.py:35): scaled keep mask on layer outputs
+                    # (seed drawn from torch's CPU generator so torch.manual_seed controls it)
+                    seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+                    mask = torch.empty_like(y)
+                    layer_in = torch.empty_like(y)
+                    _lib.call("ttr_dropout", y, y.numel(), float(p_drop), seed, layer_in, mask)
+            masks.append(mask)
     out = torch.empty(B, H, dtype=torch.float32, device=dev)
     raw = torch.empty(B, H, dtype=torch.float32, device=dev) if need_grad else None
     if enc.projection is not None:
