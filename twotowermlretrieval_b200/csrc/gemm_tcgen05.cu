@@ -5,7 +5,7 @@
 // Replaces the `X W_ih^T + b_ih` half of nn.GRU (backend/model.py:59-62) for every timestep
 // and both directions in one launch (N = dirs*3H).  Persistent: one CTA per SM walks the
 // (m, n) tile list; warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator,
-// warps 4-7 = epilogue.  The number of valid rows is read from device memory so the caller
+// warps 4-7 and 8-11 = two epilogue groups.  The number of valid rows is read from device memory so the caller
 // never synchronises on the packed token count.
 #include <cudaTypedefs.h>
 #include <cuda_fp16.h>
@@ -18,14 +18,19 @@ namespace ttr {
 constexpr int GM = 128;            // tile rows  (UMMA M)
 constexpr int GN = 128;            // tile cols  (UMMA N)
 constexpr int GK = 32;             // fp32 elements per k-block = one 128-byte swizzle row
-constexpr int G_STAGES = 6;
+constexpr int G_STAGES = 4;             // default ring depth (the kernel takes the depth as an argument)
+constexpr int G_MAX_STAGES = 6;
 constexpr int G_A_BYTES = GM * GK * 4;   // 16 KB
 constexpr int G_B_BYTES = GN * GK * 4;   // 16 KB
 constexpr int G_STAGE_BYTES = G_A_BYTES + G_B_BYTES;
 constexpr int G_ACC_COLS = GN;           // fp32 accumulator columns per buffer
 constexpr int G_TMEM_COLS = 2 * G_ACC_COLS;
-constexpr int G_THREADS = 256;
-constexpr int G_OUT_BYTES = GM * 32 * 4;   // staging buffer of one 128 x 32 output chunk: 16 KB (x2)
+constexpr int G_THREADS = 384;             // warp 0 TMA, 1 MMA, 2 TMEM alloc, 4-7 and 8-11 two epilogue groups
+constexpr int G_EPI_GROUPS = 2;            // group g drains accumulator buffer g (tiles local % 2 == g)
+constexpr int G_OUT_BYTES = GM * 32 * 4;   // staging buffer of one 128-row x 128-byte output chunk: 16 KB (x2 per group)
+constexpr int G_F16_PITCH = GN * 2 + 16;   // F16: staging row of a whole 128-column fp16 tile + 16 B (conflict-free)
+constexpr int G_F16_STAGE = GM * G_F16_PITCH;          // 34 KB per group
+__host__ __device__ constexpr int stage_area(bool f16) { return f16 ? G_F16_STAGE : 2 * G_OUT_BYTES; }   // per epilogue group
 
 extern int g_debug_flags;
 
@@ -34,20 +39,32 @@ extern int g_debug_flags;
 // the products are as exact as the tf32 ones; what changes is the traffic: operands and the 6 KB/token gi
 // row halve.  Measured with fp32 operands the kernel was bound by the SM's L2 read port on the operand
 // tiles (524 KB per 128x128x512 tile = 59 B/clk/SM) and by the output stores, not by the tensor pipe.
-template <bool F16>
+//
+// WRES = true (F16 only): "weight-stationary".  The grid is a multiple of the number of column tiles, so a
+// CTA's column tile never changes; its W tile (all k-blocks, <= 128 KB at K = 512) is loaded once and stays in
+// shared memory, and only A streams through the ring.  The operand loads were the limiter: one 128-byte row
+// segment per ~2.5-4 cycles per SM (~50 B/clk), i.e. 4.5 k / 5.5 k cycles per 128x128 tile at K = 200 / 512
+// while the MMAs need 1 k / 2 k — halving the streamed rows is worth more than a deeper ring.
+template <bool F16, bool WRES>
 __global__ void __launch_bounds__(G_THREADS, 1)
 gemm_bias_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
                       const __grid_constant__ CUtensorMap map_c, const float* __restrict__ bias, int m_bound,
-                      const int32_t* __restrict__ m_valid, int N, int K, int dbg) {
+                      const int32_t* __restrict__ m_valid, int N, int K, int dbg, void* __restrict__ c_out,
+                      int n_stages, int n_groups) {
   extern __shared__ unsigned char smem_raw[];
   // [stages][A | B]; SWIZZLE_128B atoms need 1024-byte alignment in the shared window
-  unsigned char* tiles = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
-  unsigned char* out_stage = tiles + G_STAGES * G_STAGE_BYTES;      // [2][128 rows][128 B], SWIZZLE_128B
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(out_stage + 2 * G_OUT_BYTES);
-  uint64_t* empty_bar = full_bar + G_STAGES;
-  uint64_t* acc_full = empty_bar + G_STAGES;    // [2] MMA -> epilogue
+  constexpr int GKE0 = F16 ? 2 * GK : GK;
+  const int kb_count = ceil_div(K, GKE0);
+  constexpr int STAGE_B = WRES ? G_A_BYTES : G_STAGE_BYTES;          // WRES: the ring holds A tiles only
+  unsigned char* w_res = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);   // WRES: [k_blocks][16 KB]
+  unsigned char* tiles = w_res + (WRES ? kb_count * G_B_BYTES : 0);
+  unsigned char* out_stage = tiles + n_stages * STAGE_B;            // per epilogue group
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(out_stage + n_groups * stage_area(F16));
+  uint64_t* empty_bar = full_bar + G_MAX_STAGES;
+  uint64_t* acc_full = empty_bar + G_MAX_STAGES;    // [2] MMA -> epilogue
   uint64_t* acc_empty = acc_full + 2;           // [2] epilogue -> MMA
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  uint64_t* w_full = acc_empty + 2;             // WRES: the resident W tile has landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_full + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int M = m_valid ? min(m_bound, *m_valid) : m_bound;
@@ -57,8 +74,9 @@ gemm_bias_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   const int k_blocks = ceil_div(K, GKE);
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < G_STAGES; ++s) { ptx::mbar_init(full_bar + s, 1); ptx::mbar_init(empty_bar + s, 1); }
+    for (int s = 0; s < n_stages; ++s) { ptx::mbar_init(full_bar + s, 1); ptx::mbar_init(empty_bar + s, 1); }
     for (int b = 0; b < 2; ++b) { ptx::mbar_init(acc_full + b, 1); ptx::mbar_init(acc_empty + b, 4); }
+    ptx::mbar_init(w_full, 1);
     ptx::fence_mbar_init();
   }
   if (warp == 2) {
@@ -76,18 +94,24 @@ gemm_bias_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       ptx::prefetch_tensormap(&map_a);
       ptx::prefetch_tensormap(&map_w);
     }
+    if (WRES && blockIdx.x < total_tiles && ptx::elect_one()) {
+      const int n0 = (blockIdx.x % n_tiles) * GN;         // constant for this CTA: gridDim.x % n_tiles == 0
+      ptx::mbar_arrive_expect_tx(w_full, (uint32_t)(k_blocks * G_B_BYTES));
+      for (int kb = 0; kb < k_blocks; ++kb) ptx::tma_load_2d(w_res + kb * G_B_BYTES, &map_w, kb * GKE, n0, w_full);
+    }
+    __syncwarp();
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int m0 = (tile / n_tiles) * GM, n0 = (tile % n_tiles) * GN;
       for (int kb = 0; kb < k_blocks; ++kb, ++it) {
-        const int s = it % G_STAGES;
-        const uint32_t ph = (uint32_t)(it / G_STAGES) & 1u;
+        const int s = it % n_stages;
+        const uint32_t ph = (uint32_t)(it / n_stages) & 1u;
         ptx::mbar_wait(empty_bar + s, ph ^ 1u);
-        unsigned char* a_dst = tiles + s * G_STAGE_BYTES;
+        unsigned char* a_dst = tiles + s * STAGE_B;
         if (ptx::elect_one()) {
-          ptx::mbar_arrive_expect_tx(full_bar + s, G_STAGE_BYTES);
+          ptx::mbar_arrive_expect_tx(full_bar + s, STAGE_B);
           ptx::tma_load_2d(a_dst, &map_a, kb * GKE, m0, full_bar + s);
-          ptx::tma_load_2d(a_dst + G_A_BYTES, &map_w, kb * GKE, n0, full_bar + s);
+          if (!WRES) ptx::tma_load_2d(a_dst + G_A_BYTES, &map_w, kb * GKE, n0, full_bar + s);
         }
         __syncwarp();
       }
@@ -96,6 +120,7 @@ gemm_bias_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     // ===== MMA issuer (whole warp runs the loop; one elected lane issues) =====
     constexpr uint32_t idesc = F16 ? ptx::make_idesc_f16(GM, GN) : ptx::make_idesc_tf32(GM, GN);
     int it = 0, local = 0;
+    if (WRES && blockIdx.x < total_tiles) ptx::mbar_wait(w_full, 0u);
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
       const int buf = local & 1;
       const uint32_t aph = (uint32_t)(local >> 1) & 1u;
@@ -103,13 +128,13 @@ gemm_bias_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       ptx::tc_fence_after_sync();
       const uint32_t d_tmem = tmem_base + buf * G_ACC_COLS;
       for (int kb = 0; kb < k_blocks; ++kb, ++it) {
-        const int s = it % G_STAGES;
-        const uint32_t ph = (uint32_t)(it / G_STAGES) & 1u;
+        const int s = it % n_stages;
+        const uint32_t ph = (uint32_t)(it / n_stages) & 1u;
         ptx::mbar_wait(full_bar + s, ph);
         ptx::tc_fence_after_sync();
-        const uint32_t a_addr = ptx::smem_u32(tiles + s * G_STAGE_BYTES);
+        const uint32_t a_addr = ptx::smem_u32(tiles + s * STAGE_B);
         const uint64_t a_desc = ptx::make_kmajor_sw128_desc(a_addr);
-        const uint64_t b_desc = ptx::make_kmajor_sw128_desc(a_addr + G_A_BYTES);
+        const uint64_t b_desc = ptx::make_kmajor_sw128_desc(WRES ? ptx::smem_u32(w_res + kb * G_B_BYTES) : a_addr + G_A_BYTES);
         if (ptx::elect_one()) {
 #pragma unroll
           for (int k = 0; k < GK / 8; ++k) {
@@ -129,15 +154,69 @@ gemm_bias_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     // output at 1.1 TB/s, profiles/r1_encode_breakdown_v1.txt; the copy engine writes whole
     // 128-byte row segments.)  Rows between the valid count and m_bound are written too; they
     // belong to the caller's buffer and are never read.
-    const int q = warp - 4;                               // TMEM lane quadrant of this warp
+    // Two groups of four warps alternate over the CTA's tiles (group g <-> accumulator buffer g): measured
+    // with one group the ~4.5 k cycles of tcgen05.ld / bias / staging / store per tile, not the loads or the
+    // MMAs, set the tile rate of the K = 200 layer.
+    const int grp = (warp - 4) >> 2;
+    const int q = (warp - 4) & 3;                         // TMEM lane quadrant of this warp
     const int r_in_tile = q * 32 + lane;
+    unsigned char* my_stage = out_stage + grp * stage_area(F16);
     int local = 0, chunk_no = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
       const int buf = local & 1;
+      if (n_groups == 2 ? (buf != grp) : (grp != 0)) continue;
       const uint32_t aph = (uint32_t)(local >> 1) & 1u;
       const int m0 = (tile / n_tiles) * GM, n0 = (tile % n_tiles) * GN;
       ptx::mbar_wait(acc_full + buf, aph);
       ptx::tc_fence_after_sync();
+      if constexpr (F16) {
+        // fp16 result: the whole 128 x 128 tile is staged row-major (256 B + 16 B pad per row) and written with
+        // plain coalesced stores, two full 256-byte row segments per warp instruction.  (TMA stores of
+        // 128-byte-wide boxes — the SWIZZLE_128B limit — issue one 128 B segment per row and measured
+        // 2.1 TB/s on this layout; per-thread row stores 1.1 TB/s.)
+#pragma unroll 1
+        for (int c0 = 0; c0 < GN; c0 += 32) {
+          uint32_t r[32];
+          ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * G_ACC_COLS + c0, r);
+          ptx::tmem_ld_wait();
+          if (c0 + 32 >= GN) {                            // last read of this accumulator: hand it back
+            ptx::tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(acc_empty + buf);
+          }
+          uint4* row = reinterpret_cast<uint4*>(my_stage + r_in_tile * G_F16_PITCH + c0 * 2);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {                   // four 16-byte chunks = 32 halves
+            const int n = n0 + c0 + 8 * j;
+            float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
+            if (bias && n + 7 < N) {
+              b0 = __ldg(reinterpret_cast<const float4*>(bias + n));
+              b1 = __ldg(reinterpret_cast<const float4*>(bias + n + 4));
+            }
+            const __half2 h0 = __floats2half2_rn(__uint_as_float(r[8 * j + 0]) + b0.x, __uint_as_float(r[8 * j + 1]) + b0.y);
+            const __half2 h1 = __floats2half2_rn(__uint_as_float(r[8 * j + 2]) + b0.z, __uint_as_float(r[8 * j + 3]) + b0.w);
+            const __half2 h2 = __floats2half2_rn(__uint_as_float(r[8 * j + 4]) + b1.x, __uint_as_float(r[8 * j + 5]) + b1.y);
+            const __half2 h3 = __floats2half2_rn(__uint_as_float(r[8 * j + 6]) + b1.z, __uint_as_float(r[8 * j + 7]) + b1.w);
+            row[j] = make_uint4(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1),
+                                *reinterpret_cast<const uint32_t*>(&h2), *reinterpret_cast<const uint32_t*>(&h3));
+          }
+        }
+        ptx::named_bar_sync(1 + grp, 128);
+        if (!(dbg & 2048)) {
+          __half* cbase = reinterpret_cast<__half*>(c_out);
+          const int half_lane = lane & 15, sub = lane >> 4;
+          const int ncol = n0 + 8 * half_lane;
+#pragma unroll 4
+          for (int rr = q * 32; rr < q * 32 + 32; rr += 2) {          // this warp's 32 rows, two per instruction
+            const int rrow = rr + sub;
+            const uint4 v = *reinterpret_cast<const uint4*>(my_stage + rrow * G_F16_PITCH + 16 * half_lane);
+            if (m0 + rrow < M && ncol + 7 < N)
+              *reinterpret_cast<uint4*>(cbase + (size_t)(m0 + rrow) * N + ncol) = v;
+          }
+        }
+        ptx::named_bar_sync(1 + grp, 128);                // staging is free again for this group's next tile
+        continue;
+      }
       constexpr int CW = F16 ? 64 : 32;                   // columns per 128-byte staging row
 #pragma unroll 1
       for (int c0 = 0; c0 < GN; c0 += CW, ++chunk_no) {
@@ -153,10 +232,10 @@ gemm_bias_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           __syncwarp();
           if (lane == 0) ptx::mbar_arrive(acc_empty + buf);
         }
-        unsigned char* stg = out_stage + (chunk_no & 1) * G_OUT_BYTES;
+        unsigned char* stg = my_stage + (chunk_no & 1) * G_OUT_BYTES;
         // the store that used this staging buffer two chunks ago must have finished reading it
-        if (warp == 4 && lane == 0) ptx::bulk_wait_group_read<1>();
-        ptx::named_bar_sync(1, 128);
+        if (q == 0 && lane == 0) ptx::bulk_wait_group_read<1>();
+        ptx::named_bar_sync(1 + grp, 128);
         uint4* row = reinterpret_cast<uint4*>(stg + r_in_tile * 128);
         if (!(dbg & (1 << 18)))                                       // bit 18: (timing experiment) skip bias + staging
 #pragma unroll
@@ -185,14 +264,14 @@ gemm_bias_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           row[j ^ (r_in_tile & 7)] = pk;                  // SWIZZLE_128B: 16-byte chunk index XOR (row mod 8)
         }
         ptx::fence_proxy_async_smem();
-        ptx::named_bar_sync(1, 128);
-        if (warp == 4 && lane == 0 && !(dbg & 2048)) {          // bit 11: timing experiment without the stores
+        ptx::named_bar_sync(1 + grp, 128);
+        if (q == 0 && lane == 0 && !(dbg & 2048)) {          // bit 11: timing experiment without the stores
           ptx::tma_store_2d(&map_c, stg, n0 + c0, m0);
           ptx::bulk_commit_group();
         }
       }
     }
-    if (warp == 4 && lane == 0) ptx::bulk_wait_group<0>();
+    if (q == 0 && lane == 0) ptx::bulk_wait_group<0>();
   }
 
   ptx::tc_fence_before_sync();
@@ -279,12 +358,32 @@ extern "C" int ttr_gemm_f16_bias(const void* A16, const void* W16, const float* 
   if (rc != TTR_OK) return rc;
   rc = make_f16_rowmajor_map(&map_c, C16, m_bound, N, GM);
   if (rc != TTR_OK) return rc;
-  const size_t smem = (size_t)G_STAGES * G_STAGE_BYTES + 2 * G_OUT_BYTES + (2 * G_STAGES + 4) * sizeof(uint64_t) + 16 + 1024;
-  TTR_CHECK_CUDA(cudaFuncSetAttribute(gemm_bias_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int tiles = ceil_div(m_bound, GM) * ceil_div(N, GN);
+  const int m_tiles = ceil_div(m_bound, GM), n_tiles = ceil_div(N, GN);
+  const int tiles = m_tiles * n_tiles;
+  const int k_blocks = ceil_div(K, 2 * GK);
+  const size_t misc = (2 * G_MAX_STAGES + 5) * sizeof(uint64_t) + 16 + 1024;
+  // weight-stationary when the W tile fits next to a >= 5-deep A ring and two epilogue groups (K <= 256) and every
+  // column tile gets at least one CTA; at K = 512 only a 3-deep ring would fit and that measured slower than
+  // streaming both operands through a 5-deep ring (2.29 vs 1.80 ms per 1.0 M tokens)
+  int ws_stages = 0;
+  for (int st = G_MAX_STAGES; st >= 5 && !ws_stages; --st)
+    if ((size_t)k_blocks * G_B_BYTES + (size_t)st * G_A_BYTES + 2 * stage_area(true) + misc <= 227 * 1024) ws_stages = st;
+  if (ws_stages && n_tiles <= sm_count() && !(g_debug_flags & (1 << 19))) {
+    const size_t smem_res = (size_t)k_blocks * G_B_BYTES + (size_t)ws_stages * G_A_BYTES + 2 * stage_area(true) + misc;
+    const int per_n = std::max(1, std::min(sm_count() / n_tiles, m_tiles));
+    TTR_CHECK_CUDA(cudaFuncSetAttribute(gemm_bias_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_res));
+    gemm_bias_kernel<true, true><<<n_tiles * per_n, G_THREADS, smem_res, (cudaStream_t)stream>>>(
+        map_a, map_w, map_c, bias, m_bound, m_valid, N, K, g_debug_flags, C16, ws_stages, 2);
+    TTR_CHECK_LAUNCH();
+    return TTR_OK;
+  }
+  constexpr int ST16 = 4;                  // 4 x 32 KB ring + two 34 KB staging groups (1.80 ms per 1.0 M tokens at
+                                           // K = 512; 5 stages + one group measured 2.00 ms)
+  const size_t smem = (size_t)ST16 * G_STAGE_BYTES + 2 * stage_area(true) + misc;
+  TTR_CHECK_CUDA(cudaFuncSetAttribute(gemm_bias_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int grid = std::min(tiles, sm_count());
-  gemm_bias_kernel<true><<<grid, G_THREADS, smem, (cudaStream_t)stream>>>(map_a, map_w, map_c, bias, m_bound, m_valid, N, K,
-                                                                         g_debug_flags);
+  gemm_bias_kernel<true, false><<<grid, G_THREADS, smem, (cudaStream_t)stream>>>(map_a, map_w, map_c, bias, m_bound, m_valid, N, K,
+                                                                                g_debug_flags, C16, ST16, 2);
   TTR_CHECK_LAUNCH();
   return TTR_OK;
 }
@@ -304,12 +403,13 @@ extern "C" int ttr_gemm_tf32_bias(const float* A, const float* W, const float* b
   if (rc != TTR_OK) return rc;
   rc = make_rowmajor_map(&map_c, C, m_bound, N, GM, false);
   if (rc != TTR_OK) return rc;
-  const size_t smem = (size_t)G_STAGES * G_STAGE_BYTES + 2 * G_OUT_BYTES + (2 * G_STAGES + 4) * sizeof(uint64_t) + 16 + 1024;
-  TTR_CHECK_CUDA(cudaFuncSetAttribute(gemm_bias_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  constexpr int ST32 = 6;                  // 6 x 32 KB ring + one 32 KB staging group (as measured best for tf32)
+  const size_t smem = (size_t)ST32 * G_STAGE_BYTES + stage_area(false) + (2 * G_MAX_STAGES + 5) * sizeof(uint64_t) + 16 + 1024;
+  TTR_CHECK_CUDA(cudaFuncSetAttribute(gemm_bias_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int tiles = ceil_div(m_bound, GM) * ceil_div(N, GN);
   const int grid = std::min(tiles, sm_count());
-  gemm_bias_kernel<false><<<grid, G_THREADS, smem, (cudaStream_t)stream>>>(map_a, map_w, map_c, bias, m_bound, m_valid, N, K,
-                                                                          g_debug_flags);
+  gemm_bias_kernel<false, false><<<grid, G_THREADS, smem, (cudaStream_t)stream>>>(map_a, map_w, map_c, bias, m_bound, m_valid, N, K,
+                                                                          g_debug_flags, C, ST32, 1);
   TTR_CHECK_LAUNCH();
   return TTR_OK;
 }
