@@ -293,8 +293,9 @@ def run_b200(args):
         "config": bench_config(args, world),
         "e2e": {"value": B / (ms_e2e * 1e-3), "unit": "queries/s", "h2d_bytes_per_step": B * DIM * 4,
                 "d2h_bytes_per_step": B * TOPK * 12, "ms_per_step": ms_e2e},
-        # B <= 4: streaming kernel + merge; B > 4: init, [sample scan, merge, seed,] main scan, merge; + peer merge
-        "gpu_launches": K * ((2 if B <= 4 else (6 if shard_rows >= 16 * 148 * 4 * 32 else 3)) + (2 if world > 1 else 0)),
+        # B <= 4: streaming kernel + merge; 4 < B <= 128 on shards < 4 M docs: init, fused sample+main scan,
+        # select-merge; otherwise: init, sample scan, merge, seed, main scan, merge; + barrier/peer merge at N > 1
+        "gpu_launches": K * ((2 if B <= 4 else (3 if (B <= 128 and shard_rows < 4_000_000) else 6)) + (2 if world > 1 else 0)),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                      "frac": achieved / hbm_peak, "traffic": ncu_traffic(B, shard_rows), "peak_source": peak_src,
                      "kernel": ("score_topk_stream_kernel" if B <= 4 else "score_topk_mma_kernel") +

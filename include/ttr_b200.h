@@ -155,7 +155,10 @@ int ttr_positive_rank(const float* Q, const float* docs, const int64_t* target, 
  * as FLOAT32 instead of TFLOAT32 (hardware truncation instead of round-to-nearest),
  * bit2 = force the CUDA-core streaming scorer for every batch size, bit8 = no sample pass,
  * bit9 = select-merge re-reads candidates from L2 instead of staging them in shared memory,
- * bit10 = H=256 GRU forward on the fp32 CUDA-core cluster kernel instead of the tcgen05 one. */
+ * bit10 = H=256 GRU forward on the fp32 CUDA-core cluster kernel instead of the tcgen05 one,
+ * bit11/18/19 = projection-GEMM timing experiments (no stores / no staging / no weight-stationary variant),
+ * bits12-17 = sample tiles per SM override, bit20 = per-CTA entry/exit times into the trace buffer,
+ * bit21 = never fuse the sample pass into the main scorer launch, bit22 = always fuse it. */
 int ttr_debug_set_flags(int flags);
 int ttr_debug_get_flags(int* out);
 /* Diagnostic: number of 8-CTA clusters of the tcgen05 recurrence the device holds at once. */

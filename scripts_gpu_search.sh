@@ -1,17 +1,12 @@
 #!/bin/bash
-# search-path pass: parity tests, bench at full and 1/8 corpus, ncu launch list
+# search-path pass: parity tests, bench at full and 1/8 corpus (fused and two-pass), ncu launch list
 mkdir -p gpurun_out; rm -f gpurun_out/summary.txt
-timeout 900 python -m pytest tests/test_gpu_search.py -q -m gpu -x --timeout=600 > gpurun_out/test_gpu_search.log 2>&1
+timeout 600 python -m pytest tests/test_gpu_search.py tests/test_gpu_hybrid.py -q -m gpu -x --timeout=300 > gpurun_out/test_gpu_search.log 2>&1
 echo "test_gpu_search exit $?" >> gpurun_out/summary.txt
-for cfg in "8841823 128 0" "8841823 128 65536" "8841823 128 49152" "8841823 16 0" "8841823 256 0" "1105228 128 0" "1105228 128 32768" "1105228 128 8192"; do
+for cfg in "8841823 128 0" "8841823 128 2097152" "8841823 16 0" "1105228 128 0" "1105228 128 2097152" "1105228 16 0"; do
   set -- $cfg
-  timeout 600 python bench.py --steps 10 --warmup 3 --docs $1 --batch $2 --debug-flags $3 --no-extra --no-cpu-baseline > gpurun_out/bench_d$1_b$2_f$3.log 2>&1
+  timeout 300 python bench.py --steps 10 --warmup 3 --docs $1 --batch $2 --debug-flags $3 --no-extra --no-cpu-baseline > gpurun_out/bench_d$1_b$2_f$3.log 2>&1
   echo "bench $1 $2 $3 exit $?" >> gpurun_out/summary.txt
 done
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 120 --csv --log-file gpurun_out/launches_search.csv \
-  python bench.py --steps 3 --warmup 3 --no-extra --no-cpu-baseline > gpurun_out/ncu.log 2>&1
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 120 --csv --log-file gpurun_out/launches_search_1105228.csv \
-  python bench.py --steps 3 --warmup 3 --docs 1105228 --no-extra --no-cpu-baseline > gpurun_out/ncu.log 2>&1
-echo "ncu exit $?" >> gpurun_out/summary.txt
 cat gpurun_out/summary.txt; tail -3 gpurun_out/test_gpu_search.log
-for f in gpurun_out/bench_d*_b*_f*.log; do echo $f; grep -h -o '"ms_per_step": [0-9.]*\|"frac": [0-9.]*' $f | tr '\n' ' '; echo; done
+for f in gpurun_out/bench_d*_b*_f*.log; do echo $f; grep -h -o '"ms_per_step": [0-9.]*\|"frac": [0-9.]*\|"ms_per_call": [0-9.]*' $f | tr '\n' ' '; echo; done

@@ -92,6 +92,28 @@ def test_tcgen05_and_streaming_paths_agree(cuda_device):
     assert (i_mma == i_st).float().mean() > 0.9
 
 
+def test_fused_sample_and_two_pass_paths_agree(cuda_device):
+    """B <= 128 runs sample phase, bound selection (grid barrier) and main pass in one cooperative launch;
+    debug bit 21 forces the separate sample / merge / seed launches.  Both are exact, so they agree bit for bit
+    (the bound only prunes), also with fewer than k sample candidates per query and with exact ties."""
+    from twotowermlretrieval_b200 import _lib
+    for N, B in ((200_000, 128), (150_000, 5), (400_000, 77)):       # < 4 M documents: fused by default
+        D = torch.tensor(synth.make_unit_rows(N, 256, seed=50 + B), device=cuda_device)
+        D[90_000:90_200] = D[300:500]
+        Q = torch.tensor(synth.make_unit_rows(B, 256, seed=60 + B), device=cuda_device)
+        s_a, i_a = search_topk(Q, D, 50)
+        _lib.call_nostream("ttr_debug_set_flags", 1 << 21)
+        try:
+            s_b, i_b = search_topk(Q, D, 50)
+        finally:
+            _lib.call_nostream("ttr_debug_set_flags", 0)
+        assert torch.equal(s_a, s_b) and torch.equal(i_a, i_b)
+        for _ in range(3):                                        # repeatable (the barrier counters are re-armed per call)
+            s_c, i_c = search_topk(Q, D, 50)
+            assert torch.equal(s_a, s_c) and torch.equal(i_a, i_c)
+    check_topk(s_a[:6], i_a[:6], Q[:6].cpu().numpy(), D.cpu().numpy(), 50)
+
+
 def test_select_merge_unstaged_path(cuda_device):
     """The select-merge stages candidate keys in shared memory; sets too large for that are re-read
     from L2 each radix round (debug flag bit 9 forces that path).  Same exact result either way."""

@@ -22,6 +22,11 @@ _lib.call_nostream("ttr_debug_set_trace", None)
 _lib.call_nostream("ttr_debug_set_flags", 0)
 t = tr.cpu().numpy().reshape(8, 256)
 t0 = t[0, 0]
+mk = t[:5, 255]
+print("kernel marks (cycles from entry): prologue_done %d, first_tma_issue %d, last_tile_filtered %d, published %d, exit %d" %
+      (mk[1] - mk[0], t0 - mk[0], mk[2] - mk[0], mk[3] - mk[0], mk[4] - mk[0]))
+ntile = -(-N // 32 + 147) // 148
+print("tiles per CTA ~", ntile, "; cycles from first TMA issue to last filtered:", mk[2] - t0)
 names = ["prod_issue", "mma_full", "mma_issued", "epi_accfull", "epi_release", "mma_done", "epi_loop_end", "epi_tile_end"]
 print("tile " + " ".join(f"{n:>12}" for n in names))
 for i in list(range(0, 12)) + list(range(100, 112)):

@@ -26,6 +26,8 @@
 // cycles per round, 3 stages: 1850 cycles per tile); this is v4.
 #include <cudaTypedefs.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 #include "ptx.cuh"
 #include "topk_common.cuh"
@@ -179,9 +181,10 @@ constexpr int SM_TRACE_TILES = 256;   // trace buffer: 8 roles x 256 tiles
       trace[(role) * SM_TRACE_TILES + _ti] = clock64();                                         \
   } while (0)
 
-__global__ void init_tau_kernel(float* tau, int32_t* qcount, int n) {
+__global__ void init_tau_kernel(float* tau, int32_t* qcount, int n, unsigned int* counters) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) { tau[i] = -INFINITY; qcount[i] = 0; }
+  if (i < 2 && counters) counters[i] = 0u;
 }
 
 // tau[q] = k-th best score of the sample pass (a valid lower bound on the final k-th best)
@@ -190,6 +193,67 @@ __global__ void seed_tau_kernel(float* tau, int32_t* qcount, const float* __rest
   int q = blockIdx.x * blockDim.x + threadIdx.x;
   if (q < n_pad) qcount[q] = 0;
   if (q < B && sample_i[(int64_t)q * k + (k - 1)] >= 0) tau[q] = sample_s[(int64_t)q * k + (k - 1)];
+}
+
+// k-th largest of n floats in global memory (fused sample phase), computed by the 128 epilogue threads of a
+// CTA (named barrier 2): keys staged in `smem_f` (n <= SM_CAP * SM_MQ), MSD radix select over the
+// order-preserving 32-bit keys, 8 bits per round.  Returns -inf when fewer than k finite values exist.
+__device__ __forceinline__ float kth_largest_128(float* smem_f, const float* __restrict__ src, int n, int k, int tid) {
+  __shared__ uint32_t hist[256];
+  __shared__ uint32_t s_prefix, s_rem;
+  uint32_t* keys = reinterpret_cast<uint32_t*>(smem_f);
+  int finite = 0;
+  for (int i = tid; i < n; i += SM_MQ) {
+    const float v = __ldcg(src + i);
+    keys[i] = f2key(v);
+    finite += v > -INFINITY ? 1 : 0;
+  }
+  if (tid == 0) { s_prefix = 0u; s_rem = (uint32_t)k; }
+  // count finite values across the 128 threads through the histogram array
+  if (tid < 256 / 2) { hist[tid] = 0u; hist[tid + 128] = 0u; }
+  ptx::named_bar_sync(2, SM_MQ);
+  atomicAdd(&hist[0], (uint32_t)finite);
+  ptx::named_bar_sync(2, SM_MQ);
+  const bool enough = hist[0] >= (uint32_t)k;
+  ptx::named_bar_sync(2, SM_MQ);
+  if (!enough) return -INFINITY;
+  for (int shift = 24; shift >= 0; shift -= 8) {
+    hist[tid] = 0u; hist[tid + 128] = 0u;
+    ptx::named_bar_sync(2, SM_MQ);
+    const uint32_t prefix = s_prefix;
+    const uint32_t hi_mask = shift == 24 ? 0u : (0xffffffffu << (shift + 8));
+    for (int i = tid; i < n; i += SM_MQ) {
+      const uint32_t key = keys[i];
+      if ((key & hi_mask) == (prefix & hi_mask)) atomicAdd(&hist[(key >> shift) & 255u], 1u);
+    }
+    ptx::named_bar_sync(2, SM_MQ);
+    if (tid < 32) {
+      uint32_t h[8], own = 0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { h[j] = hist[8 * tid + j]; own += h[j]; }
+      uint32_t suf = own;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t v = __shfl_down_sync(0xffffffffu, suf, d);
+        if (tid + d < 32) suf += v;
+      }
+      const uint32_t above = suf - own, rem = s_rem;
+      __syncwarp();
+      if (above < rem && rem <= suf) {
+        uint32_t cum = above;
+#pragma unroll
+        for (int j = 7; j >= 0; --j) {
+          if (cum < rem && rem <= cum + h[j]) {
+            s_prefix = (prefix & hi_mask) | ((uint32_t)(8 * tid + j) << shift);
+            s_rem = rem - cum;
+          }
+          cum += h[j];
+        }
+      }
+    }
+    ptx::named_bar_sync(2, SM_MQ);
+  }
+  return key2f(s_prefix);
 }
 
 // Scratch layout per CTA c = slice * n_qt + qt (thread ql = query inside the tile):
@@ -207,12 +271,28 @@ __global__ void seed_tau_kernel(float* tau, int32_t* qcount, const float* __rest
 // bound on the final k-th best (every published candidate is a real document), and it equals the
 // exact k-th best of the sample unless one CTA holds more than SM_SAMPLE_TOP of the sample's top k
 // (256 documents of ~38 k per CTA: mean 0.34 of the top 50).
-template <bool SAMPLE>
+//
+// MODE 2 (one query tile, all CTAs co-resident — cooperative launch) fuses the two passes into one launch:
+// every CTA first runs its sample tiles through the register top-8 path and writes them to a fixed slot of
+// `samp` ([query][slice][8]); a grid-wide barrier; CTA q (q < B) radix-selects the k-th best of query q's
+// n_slices * 8 sample scores into tau_g[q]; a second barrier; then the main pass over ALL tiles with the seeded
+// bound.  The TMA and MMA warps simply keep running ahead into the main tiles while the barriers pass.  This
+// removes a kernel launch with its ~30 us of fixed cost (TMEM allocation, query staging, pipeline fill, drain),
+// the sample merge and the seed kernel: what limits an eighth-of-the-corpus shard (173 us of HBM time).
+struct FusedArgs {
+  float* samp;              // [128][n_slices * SM_SAMPLE_TOP] sample scores
+  unsigned int* counters;   // two grid-barrier counters, zeroed before the launch
+  int sample_tiles;         // tiles per CTA in the sample phase
+};
+
+template <int MODE>
 __global__ void __launch_bounds__(SM_THREADS, 1)
 score_topk_mma_kernel(const float* __restrict__ Q, const __grid_constant__ CUtensorMap map_d, int B, int64_t N,
                       int k, int n_slices, float* __restrict__ tau_g, float* __restrict__ out_s,
                       int32_t* __restrict__ out_i, int32_t* __restrict__ out_n, long long* __restrict__ trace,
-                      int dbg) {
+                      int dbg, FusedArgs fa) {
+  constexpr bool SAMPLE = MODE == 1;
+  constexpr bool FUSED = MODE == 2;
   extern __shared__ unsigned char smem_raw[];
   unsigned char* base = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
   unsigned char* ring = base;                                      // [stages][SM_KB][32 rows][128 B]
@@ -226,11 +306,27 @@ score_topk_mma_kernel(const float* __restrict__ Q, const __grid_constant__ CUten
   __shared__ uint64_t probe_bar;             // dbg & 64: the MMA warp waits for its own commit (timing experiment)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#define SM_MARK(slot)                                                                                   \
+  do {                                                                                                  \
+    if (trace && blockIdx.x == 0 && blockIdx.y == 0) trace[(slot) * SM_TRACE_TILES + SM_TRACE_TILES - 1] = clock64(); \
+  } while (0)
+  if (threadIdx.x == 0) SM_MARK(0);          // kernel entry (slots use the last column of the trace rows)
+  // dbg bit 20: instead of the tile timeline, rows 5/6 of the trace receive every CTA's entry / exit globaltimer (ns)
+  if (trace && (dbg & (1 << 20)) && threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y < SM_TRACE_TILES) {
+    long long gt;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+    trace[5 * SM_TRACE_TILES + blockIdx.y] = gt;
+  }
   const int qt = blockIdx.x;                 // query tile
   const int slice = blockIdx.y;              // document slice
   const int q0 = qt * SM_MQ;
   const int64_t n_tiles = ceil_div64(N, (int64_t)SM_ND);
   const int cta = slice * gridDim.x + qt;
+  // this CTA's tile sequence: [FUSED: its first S tiles once more in front,] then tiles slice, slice + n_slices, ...
+  const int n_mine = slice < n_tiles ? (int)((n_tiles - slice + n_slices - 1) / n_slices) : 0;
+  const int S = FUSED ? fa.sample_tiles : 0;
+  const int n_seq = n_mine + S;
+  auto tile_at = [&](int it) -> int64_t { return (int64_t)slice + (int64_t)(it < S ? it : it - S) * n_slices; };
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < SM_STAGES; ++s) { ptx::mbar_init(full_bar + s, 1); ptx::mbar_init(empty_bar + s, 1); }
@@ -280,11 +376,12 @@ score_topk_mma_kernel(const float* __restrict__ Q, const __grid_constant__ CUten
   __syncthreads();
   ptx::tc_fence_after_sync();
 
+  if (threadIdx.x == 0) SM_MARK(1);          // prologue done (TMEM allocated, queries staged)
   if (warp == 0) {
     // ===== TMA producer (whole warp runs the loop; one elected lane issues) =====
     if (ptx::elect_one()) ptx::prefetch_tensormap(&map_d);
-    int it = 0;
-    for (int64_t t = slice; t < n_tiles; t += n_slices, ++it) {
+    for (int it = 0; it < n_seq; ++it) {
+      const int64_t t = tile_at(it);
       const int s = it % SM_STAGES;
       const uint32_t ph = (uint32_t)(it / SM_STAGES) & 1u;
       ptx::mbar_wait(empty_bar + s, ph ^ 1u);
@@ -302,8 +399,8 @@ score_topk_mma_kernel(const float* __restrict__ Q, const __grid_constant__ CUten
   } else if (warp == 1) {
     // ===== MMA issuer (whole warp runs the loop; one elected lane issues) =====
     constexpr uint32_t idesc = ptx::make_idesc_tf32(SM_MQ, SM_ND);
-    int it = 0;
-    for (int64_t t = slice; t < n_tiles; t += n_slices, ++it) {
+    for (int it = 0; it < n_seq; ++it) {
+      const int64_t t = tile_at(it);
       const int s = it % SM_STAGES;
       const uint32_t ph = (uint32_t)(it / SM_STAGES) & 1u;
       const int buf = it % SM_NACC;
@@ -359,12 +456,16 @@ score_topk_mma_kernel(const float* __restrict__ Q, const __grid_constant__ CUten
     int it = 0;
     // Global lower bound on the k-th best.  An L2 read under a saturated memory system costs
     // microseconds, so it is refreshed every 8 tiles and consumed one refresh later.
-    float tg = q_valid ? __ldcg(tau_g + q) : INFINITY;     // seeded by the sample pass (or -inf)
+    float tg = (q_valid && !FUSED) ? __ldcg(tau_g + q) : (q_valid ? -INFINITY : INFINITY);   // seeded by the sample pass (or -inf)
     float tg_pending = tg;
-    for (int64_t t = slice; t < n_tiles; t += n_slices, ++it) {
+    // one tile of the epilogue; `smp` (compile-time) selects the register top-8 path of the sample phase.  Two
+    // instantiations instead of a runtime flag: with the flag in the loop the main pass ran 10 % slower.
+    auto tile_body = [&](const int it, auto smp_tag) {
+      constexpr bool smp = decltype(smp_tag)::value;
+      const int64_t t = tile_at(it);
       const int buf = it % SM_NACC;
       const uint32_t aph = (uint32_t)(it / SM_NACC) & 1u;
-      if ((it & 7) == 0 && q_valid) {
+      if ((it & 7) == 0 && q_valid && !smp) {
         tg = fmaxf(tg, tg_pending);
         tg_pending = __ldcg(tau_g + q);
       }
@@ -398,8 +499,8 @@ score_topk_mma_kernel(const float* __restrict__ Q, const __grid_constant__ CUten
       if (qw == 0) SM_TRACE(4, it);
       const int64_t d0 = t * SM_ND;
       // one threshold, one compare per score: "strictly above tau" == ">= next float above tau"
-      const float thr = SAMPLE ? key2f(f2key(top_s[SM_SAMPLE_TOP - 1]) + 1u)      // must beat the weakest kept score
-                               : fmaxf(tg, strict ? key2f(f2key(tau) + 1u) : tau);
+      const float thr = smp ? key2f(f2key(top_s[SM_SAMPLE_TOP - 1]) + 1u)         // must beat the weakest kept score
+                            : fmaxf(tg, strict ? key2f(f2key(tau) + 1u) : tau);
       // Branch-free filter -> per-lane bit mask of surviving documents.  (A short-circuit
       // condition compiles to a branch per score: ~45 cycles of resolve latency each with one
       // warp per scheduler, 1300-1600 cycles per tile; profiles/r1_score_topk_mma_v4_trace_*.)
@@ -424,7 +525,7 @@ score_topk_mma_kernel(const float* __restrict__ Q, const __grid_constant__ CUten
           SM_CASE(24) SM_CASE(25) SM_CASE(26) SM_CASE(27) SM_CASE(28) SM_CASE(29) SM_CASE(30) SM_CASE(31)
 #undef SM_CASE
         }
-        if (SAMPLE) {
+        if (smp) {
           // bubble the candidate through the sorted registers; lanes whose score did not pass carry -inf
           float cs = ((mask >> j) & 1u) ? scj : -INFINITY;
           int32_t ci = (int32_t)(d0 + j);
@@ -440,18 +541,52 @@ score_topk_mma_kernel(const float* __restrict__ Q, const __grid_constant__ CUten
           }
         } else if ((mask >> j) & 1u) {   // cnt <= SM_CAP - SM_ND before the tile, so 32 free slots exist
           ls[cnt * SM_MQ] = scj;
-          li[cnt * SM_MQ] = (uint16_t)(it * SM_ND + j);
+          li[cnt * SM_MQ] = (uint16_t)((it - S) * SM_ND + j);
           ++cnt;
         }
       }
       if (qw == 0) SM_TRACE(6, it);
-      if (!SAMPLE && __any_sync(0xffffffffu, cnt > SM_CAP - SM_ND)) {
+      if (!smp && __any_sync(0xffffffffu, cnt > SM_CAP - SM_ND)) {
         __syncwarp();
         cnt = thread_compact(ls, li, cnt, k, tau, strict);
         if (q_valid && cnt >= k) atomic_max_float(tau_g + q, tau);
       }
       if (qw == 0) SM_TRACE(7, it);
+    };
+    if (FUSED) {
+      for (it = 0; it < S; ++it) tile_body(it, std::true_type{});
+        // ---- end of the sample phase: publish, grid barrier, CTA q selects query q's bound, grid barrier ----
+        float* mine = fa.samp + ((size_t)ql * n_slices + slice) * SM_SAMPLE_TOP;
+#pragma unroll
+        for (int e = 0; e < SM_SAMPLE_TOP; ++e) mine[e] = (q_valid && top_i[e] >= 0) ? top_s[e] : -INFINITY;
+        __threadfence();
+        ptx::named_bar_sync(2, SM_MQ);
+        if (ql == 0) {
+          atomicAdd(fa.counters, 1u);
+          while (*reinterpret_cast<volatile unsigned int*>(fa.counters) < (unsigned)n_slices) __nanosleep(64);
+          __threadfence();
+        }
+        ptx::named_bar_sync(2, SM_MQ);
+        if (slice < B) {
+          const float kth = kth_largest_128(list_s, fa.samp + (size_t)slice * n_slices * SM_SAMPLE_TOP,
+                                            n_slices * SM_SAMPLE_TOP, k, ql);
+          if (ql == 0) tau_g[slice] = kth;
+          __threadfence();
+        }
+        ptx::named_bar_sync(2, SM_MQ);
+        if (ql == 0) {
+          atomicAdd(fa.counters + 1, 1u);
+          while (*reinterpret_cast<volatile unsigned int*>(fa.counters + 1) < (unsigned)n_slices) __nanosleep(64);
+          __threadfence();
+        }
+        ptx::named_bar_sync(2, SM_MQ);
+        tg = q_valid ? __ldcg(tau_g + q) : INFINITY;
+        tg_pending = tg;
+      for (; it < n_seq; ++it) tile_body(it, std::false_type{});
+    } else {
+      for (it = 0; it < n_seq; ++it) tile_body(it, std::integral_constant<bool, SAMPLE>{});
     }
+    if (threadIdx.x == 128) SM_MARK(2);      // last tile filtered
     if (SAMPLE) {
       if (q_valid) {
         int n_keep = 0;
@@ -482,9 +617,17 @@ score_topk_mma_kernel(const float* __restrict__ Q, const __grid_constant__ CUten
     }
   }
 
+  if (threadIdx.x == 128) SM_MARK(3);        // candidates published
   ptx::tc_fence_before_sync();
   __syncthreads();
   if (warp == 2) ptx::tmem_dealloc(tmem_base, SM_TMEM_COLS);
+  if (threadIdx.x == 0) SM_MARK(4);          // kernel exit
+  if (trace && (dbg & (1 << 20)) && threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y < SM_TRACE_TILES) {
+    long long gt;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+    trace[6 * SM_TRACE_TILES + blockIdx.y] = gt;
+  }
+#undef SM_MARK
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -676,7 +819,7 @@ static int launch_select_merge(const float* outs, const int32_t* outi, const int
 
 struct MmaPlan {
   int n_qt, n_slices, n_ctas;
-  int64_t tau_off, outs_off, outi_off, outn_off, total;
+  int64_t tau_off, outs_off, outi_off, outn_off, samp_off, cnt_off, total;
 };
 
 MmaPlan mma_plan(int B, int64_t N) {
@@ -694,7 +837,9 @@ MmaPlan mma_plan(int B, int64_t N) {
   p.outs_off = align(bp * 4);
   p.outi_off = align(p.outs_off + (int64_t)p.n_ctas * SM_KEEP * SM_MQ * 4);
   p.outn_off = align(p.outi_off + (int64_t)p.n_ctas * SM_KEEP * SM_MQ * 4);
-  p.total = align(p.outn_off + bp * 4);
+  p.samp_off = align(p.outn_off + bp * 4);                                   // fused mode: [128][n_slices][8] fp32
+  p.cnt_off = align(p.samp_off + (int64_t)SM_MQ * p.n_slices * SM_SAMPLE_TOP * 4);
+  p.total = align(p.cnt_off + 16);
   return p;
 }
 
@@ -707,11 +852,15 @@ int launch_score_topk_mma(const float* Q, int B, const float* docs, int64_t N, i
   int32_t* outi = reinterpret_cast<int32_t*>(ws + p.outi_off);
   int32_t* outn = reinterpret_cast<int32_t*>(ws + p.outn_off);
   const int nq_pad = p.n_qt * SM_MQ;
-  init_tau_kernel<<<ceil_div(nq_pad, 256), 256, 0, st>>>(tau, outn, nq_pad);
+  float* samp = reinterpret_cast<float*>(ws + p.samp_off);
+  unsigned int* counters = reinterpret_cast<unsigned int*>(ws + p.cnt_off);
+  init_tau_kernel<<<ceil_div(nq_pad, 256), 256, 0, st>>>(tau, outn, nq_pad, counters);
   TTR_CHECK_LAUNCH();
   const size_t smem = (size_t)SM_STAGES * SM_STAGE_BYTES + SM_LIST_BYTES + SM_LISTI_BYTES + (2 * SM_STAGES + 2 * SM_NACC) * 8 + 16 + 1024;
-  TTR_CHECK_CUDA(cudaFuncSetAttribute(score_topk_mma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  TTR_CHECK_CUDA(cudaFuncSetAttribute(score_topk_mma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  TTR_CHECK_CUDA(cudaFuncSetAttribute(score_topk_mma_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  TTR_CHECK_CUDA(cudaFuncSetAttribute(score_topk_mma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  TTR_CHECK_CUDA(cudaFuncSetAttribute(score_topk_mma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const FusedArgs no_fuse{nullptr, nullptr, 0};
   // Sample pass: exact top-k of the first ~38 k documents gives every query a k-th-best bound
   // (top ~0.1 %) before the full scan starts.  Without it each CTA spends its first ~250
   // tiles appending and compacting almost everything it sees (3-4 k cycles per tile instead
@@ -723,14 +872,40 @@ int launch_score_topk_mma(const float* Q, int B, const float* docs, int64_t N, i
   // 0.295 -> 0.275 ms per 128-query step)
   const int tiles_override = (g_debug_flags >> 12) & 63;          // bits 12-17: sample tiles per SM (experiments)
   const int64_t n_sample = (int64_t)sm_count() * (tiles_override ? tiles_override : (N >= 4000000 ? 16 : 8)) * SM_ND;
+  const int sample_tiles = (int)(n_sample / SM_ND / sm_count());
+  // one query tile and one CTA per SM: sample phase, bound selection and main pass in ONE cooperative launch
+  static int fused_ok = -1;                   // -1 unknown, 0 the device refused the cooperative launch once
+  // (measured: 0.263 vs 0.274 ms per 128-query step on a 1.1 M-document shard, no difference on 8.8 M documents,
+  // where the two-pass path stays the default; debug bit 22 forces the fused launch there too)
+  const bool fuse_size = N < 4000000 || (g_debug_flags & (1 << 22));
+  if (N >= 16 * n_sample && !(g_debug_flags & (256 | (1 << 21))) && p.n_qt == 1 && p.n_slices <= sm_count() && B <= p.n_slices &&
+      fused_ok != 0 && fuse_size) {
+    CUtensorMap map_f;
+    int rcf = make_tf32_rowmajor_map(&map_f, docs, N, SM_DIM, SM_ND);
+    if (rcf != TTR_OK) return rcf;
+    FusedArgs fa{samp, counters, sample_tiles};
+    long long* tr = g_score_trace;
+    int dbgv = g_debug_flags;
+    int n_sl = p.n_slices;
+    void* args[] = {(void*)&Q, (void*)&map_f, (void*)&B, (void*)&N, (void*)&k, (void*)&n_sl, (void*)&tau, (void*)&outs,
+                    (void*)&outi, (void*)&outn, (void*)&tr, (void*)&dbgv, (void*)&fa};
+    cudaError_t ce = cudaLaunchCooperativeKernel((const void*)score_topk_mma_kernel<2>, dim3(1, p.n_slices), dim3(SM_THREADS),
+                                                 args, smem, st);
+    if (ce == cudaSuccess) {
+      fused_ok = 1;
+      return launch_select_merge(outs, outi, outn, B, p.n_slices, k, row_offset, out_scores, out_idx, st);
+    }
+    (void)cudaGetLastError();                 // not co-resident on this device/partition: use the two-pass path
+    fused_ok = 0;
+  }
   if (N >= 16 * n_sample && !(g_debug_flags & 256)) {
     MmaPlan ps = mma_plan(B, n_sample);
     CUtensorMap map_s;
     int rc = make_tf32_rowmajor_map(&map_s, docs, n_sample, SM_DIM, SM_ND);
     if (rc != TTR_OK) return rc;
     dim3 gs(ps.n_qt, ps.n_slices);
-    score_topk_mma_kernel<true><<<gs, SM_THREADS, smem, st>>>(Q, map_s, B, n_sample, k, ps.n_slices, tau, outs, outi,
-                                                             outn, nullptr, g_debug_flags);
+    score_topk_mma_kernel<1><<<gs, SM_THREADS, smem, st>>>(Q, map_s, B, n_sample, k, ps.n_slices, tau, outs, outi,
+                                                          outn, nullptr, g_debug_flags, no_fuse);
     TTR_CHECK_LAUNCH();
     rc = launch_select_merge(outs, outi, outn, B, ps.n_slices, k, 0, out_scores, out_idx, st);
     if (rc != TTR_OK) return rc;
@@ -741,8 +916,8 @@ int launch_score_topk_mma(const float* Q, int B, const float* docs, int64_t N, i
   int rc = make_tf32_rowmajor_map(&map_d, docs, N, SM_DIM, SM_ND);
   if (rc != TTR_OK) return rc;
   dim3 grid(p.n_qt, p.n_slices);
-  score_topk_mma_kernel<false><<<grid, SM_THREADS, smem, st>>>(Q, map_d, B, N, k, p.n_slices, tau, outs, outi, outn,
-                                                               g_score_trace, g_debug_flags);
+  score_topk_mma_kernel<0><<<grid, SM_THREADS, smem, st>>>(Q, map_d, B, N, k, p.n_slices, tau, outs, outi, outn,
+                                                           g_score_trace, g_debug_flags, no_fuse);
   TTR_CHECK_LAUNCH();
   return launch_select_merge(outs, outi, outn, B, p.n_slices, k, row_offset, out_scores, out_idx, st);
 }
