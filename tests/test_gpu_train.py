@@ -125,6 +125,40 @@ def test_cfgdims_two_fused_steps_match_reference(cuda_device):
             np.testing.assert_allclose(v.reshape(-1)[:64].cpu().numpy(), g[f"ah::{k}"], rtol=1e-3, atol=2e-5, err_msg=k)
 
 
+def test_tcgen05_bptt_matches_fp32_kernel_and_is_repeatable(cuda_device):
+    """Config dims, 300 passages (three 128-row cluster tiles, ragged lengths, both directions, two layers):
+    gradients of the tcgen05 split-K BPTT vs the fp32 CUDA-core BPTT (debug bit 23) on the same forward, and
+    run-to-run stability of the tcgen05 path.  The 8 partial products of a cluster are added by the copy
+    engine in arrival order (as are the split-K partials of the weight-gradient GEMMs), so repeats agree to fp32
+    reassociation noise (measured 3.5e-5 of the tensor scale), not bit for bit;
+    a protocol race would show up orders of magnitude above that."""
+    cfg = synth.default_config(vocab_size=5000, embed_dim=200)
+    cfg["DROPOUT"] = 0.0
+    sd_np = synth.make_state_dict(cfg, seed=5, table_seed=6)
+    ids, _ = synth.make_tokens(300, "passage", 5000, seed=31)
+    qids, _ = synth.make_tokens(300, "query", 5000, seed=32)
+    x, xq = torch.tensor(ids, device=cuda_device), torch.tensor(qids, device=cuda_device)
+
+    def grads(flag):
+        m = model_from_numpy(cfg, sd_np, cuda_device).train()
+        _lib.call_nostream("ttr_debug_set_flags", flag)
+        try:
+            d, q = m.encode_document(x), m.encode_query(xq)
+            loss = triplet_loss_cosine((q, d, d.roll(1, 0)), margin=0.5) + (d * d.roll(2, 0)).sum() * 1e-3
+            loss.backward()
+        finally:
+            _lib.call_nostream("ttr_debug_set_flags", 0)
+        return {k: p.grad.detach().clone() for k, p in m.named_parameters() if p.grad is not None}
+
+    g_tc, g_tc2, g_ref = grads(0), grads(0), grads(1 << 23)
+    assert set(g_tc) == set(g_ref) and len(g_tc) > 10
+    for k in g_ref:
+        scale = float(g_ref[k].abs().max())
+        assert float((g_tc[k] - g_tc2[k]).abs().max()) <= 2e-4 * max(scale, 1e-12), k
+        err = float((g_tc[k] - g_ref[k]).abs().max())
+        assert err <= 2e-3 * max(scale, 1e-12), (k, err, scale)
+
+
 def test_clip_adam_kernel_vs_torch(cuda_device):
     torch.manual_seed(0)
     n = 100003

@@ -37,6 +37,7 @@ _SIGNATURES = {
     "ttr_gru_recurrence_fwd_f16": [P, P, P, P, P, I32, I32, I32, P, P, P, I64, P],
     "ttr_gemm_f16_bias": [P, P, P, P, I32, P, I32, I32, P],
     "ttr_f32_to_f16": [P, P, I64, P],
+    "ttr_gru_recurrence_bwd_ws": [P, P, P, P, P, P, P, I32, I32, I32, P, P, P, I64, P],
     "ttr_gru_recurrence_bwd": [P, P, P, P, P, P, P, I32, I32, I32, P, P, P],
     "ttr_gru_whh_grad": [P, P, P, I32, I32, I32, I32, P, P, I32, P],
     "ttr_proj_l2norm_fwd": [P, P, P, I32, I32, I32, I32, P, P, P],
@@ -57,7 +58,8 @@ _SIGNATURES = {
 }
 
 EXPORTED_SYMBOLS = sorted(list(_SIGNATURES) + ["ttr_last_error", "ttr_version", "ttr_score_topk_workspace_bytes",
-                                               "ttr_blend_topk_workspace_bytes", "ttr_gru_fwd_workspace_bytes"])
+                                               "ttr_blend_topk_workspace_bytes", "ttr_gru_fwd_workspace_bytes",
+                                               "ttr_gru_bwd_workspace_bytes"])
 
 _lib = None
 
@@ -85,6 +87,8 @@ def load() -> ctypes.CDLL:
     lib.ttr_blend_topk_workspace_bytes.argtypes = [I32]
     lib.ttr_gru_fwd_workspace_bytes.restype = ctypes.c_int64
     lib.ttr_gru_fwd_workspace_bytes.argtypes = [I32, I32, I32]
+    lib.ttr_gru_bwd_workspace_bytes.restype = ctypes.c_int64
+    lib.ttr_gru_bwd_workspace_bytes.argtypes = [I32, I32, I32]
     for name, args in _SIGNATURES.items():
         fn = getattr(lib, name)
         fn.restype = ctypes.c_int

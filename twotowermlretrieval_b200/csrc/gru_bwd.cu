@@ -287,7 +287,35 @@ gru_hprev_kernel(const float* __restrict__ y, const int32_t* __restrict__ offset
   }
 }
 
+int64_t gru_bwd_tc_workspace_bytes(int B, int dirs);
+int launch_gru_bwd_tc(const float* dy, const float* dh_last, const float* y, const float* saved, const float* w_hh,
+                      const int32_t* order, const int32_t* offsets, int B, int dirs, float* dgi, float* dgh,
+                      void* workspace, cudaStream_t st);
+
 }  // namespace ttr
+
+extern "C" int64_t ttr_gru_bwd_workspace_bytes(int B, int H, int dirs) {
+  return H == ttr::BH ? ttr::gru_bwd_tc_workspace_bytes(B, dirs) : 0;
+}
+
+extern "C" int ttr_gru_recurrence_bwd(const float* dy, const float* dh_last, const float* y, const float* saved,
+                                      const float* w_hh, const int32_t* order, const int32_t* offsets, int B, int H,
+                                      int dirs, float* dgi, float* dgh, void* stream);
+
+extern "C" int ttr_gru_recurrence_bwd_ws(const float* dy, const float* dh_last, const float* y, const float* saved,
+                                         const float* w_hh, const int32_t* order, const int32_t* offsets, int B, int H,
+                                         int dirs, float* dgi, float* dgh, void* workspace, int64_t workspace_bytes,
+                                         void* stream) {
+  using namespace ttr;
+  TTR_REQUIRE(B >= 1 && H >= 1 && (dirs == 1 || dirs == 2), "ttr_gru_recurrence_bwd_ws: bad shape");
+  TTR_REQUIRE(y && saved && dgi && dgh, "ttr_gru_recurrence_bwd_ws: y, saved, dgi, dgh are required");
+  if (H == BH && workspace != nullptr && !(g_debug_flags & (1 | (1 << 23)))) {
+    TTR_REQUIRE(workspace_bytes >= gru_bwd_tc_workspace_bytes(B, dirs), "ttr_gru_recurrence_bwd_ws: workspace of %lld B < %lld B",
+                (long long)workspace_bytes, (long long)gru_bwd_tc_workspace_bytes(B, dirs));
+    return launch_gru_bwd_tc(dy, dh_last, y, saved, w_hh, order, offsets, B, dirs, dgi, dgh, workspace, (cudaStream_t)stream);
+  }
+  return ttr_gru_recurrence_bwd(dy, dh_last, y, saved, w_hh, order, offsets, B, H, dirs, dgi, dgh, stream);
+}
 
 extern "C" int ttr_gru_recurrence_bwd(const float* dy, const float* dh_last, const float* y, const float* saved,
                                       const float* w_hh, const int32_t* order, const int32_t* offsets, int B, int H,

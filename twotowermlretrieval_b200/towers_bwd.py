@@ -4,7 +4,7 @@
   ttr_l2norm_bwd            through F.normalize
   gemm_nn / gemm_tn / colsum through the projection Linear
   per layer, top down:
-    ttr_gru_recurrence_bwd  BPTT -> d(gi), d(gh) per token
+    ttr_gru_recurrence_bwd_ws  BPTT -> d(gi), d(gh) per token (tcgen05 split-K for H = 256)
     ttr_gru_whh_grad        dW_hh = d(gh)^T h_prev
     ttr_gemm_tn_fp32        dW_ih = d(gi)^T layer_input
     ttr_colsum              db_ih, db_hh
@@ -68,8 +68,10 @@ def encoder_backward(enc, ctx: dict, d_out: torch.Tensor) -> List[Optional[torch
         in_dim = W_ih.shape[1]
         dgi = torch.empty(Mb, G, dtype=torch.float32, device=dev)
         dgh = torch.empty(Mb, G, dtype=torch.float32, device=dev)
-        _lib.call("ttr_gru_recurrence_bwd", dy, dh_last, ctx["ys"][layer], ctx["saveds"][layer], W_hh,
-                  plan.order, plan.offsets, B, H, dirs, dgi, dgh)
+        ws_bytes = int(_lib.load().ttr_gru_bwd_workspace_bytes(B, H, dirs))
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev) if ws_bytes else None
+        _lib.call("ttr_gru_recurrence_bwd_ws", dy, dh_last, ctx["ys"][layer], ctx["saveds"][layer], W_hh,
+                  plan.order, plan.offsets, B, H, dirs, dgi, dgh, ws, ws_bytes)
         # weight gradients on the tensor cores (tf32, token dimension reduced with split-K); the
         # operands' rows between the valid token count and the next multiple of 32 must be zero
         layer_in = ctx["layer_ins"][layer]
