@@ -133,12 +133,15 @@ int ttr_gru_recurrence_bwd(const float* dy, const float* dh_last, const float* y
  * (0 for H != 256; contents irrelevant): H == 256 then runs the tcgen05 BPTT — d(gh) W_hh as a split-K
  * product over the 8 CTAs of a cluster (fp16 hi/lo planes of the scaled gate gradients, fp16 W_hh, fp32
  * accumulation), partials reduce-added into the scratch by the copy engine.  Debug bit 23 keeps the fp32
- * CUDA-core kernel. */
+ * CUDA-core kernel.  db_ih / db_hh (optional, fp32 [dirs*3H]) RECEIVE += the bias gradients (column sums
+ * of dgi / dgh over the valid tokens; m_bound / m_valid as in ttr_colsum): fused into the tcgen05 kernel,
+ * a ttr_colsum call after the others. */
 int64_t ttr_gru_bwd_workspace_bytes(int B, int H, int dirs);
 int ttr_gru_recurrence_bwd_ws(const float* dy, const float* dh_last, const float* y,
                               const float* saved, const float* w_hh, const int32_t* order,
                               const int32_t* offsets, int B, int H, int dirs, float* dgi, float* dgh,
-                              void* workspace, int64_t workspace_bytes, void* stream);
+                              void* workspace, int64_t workspace_bytes, int m_bound,
+                              const int32_t* m_valid, float* db_ih, float* db_hh, void* stream);
 /* dW_hh[dir] (+)= dgh[:, dir]^T h_prev[:, dir], where h_prev is y shifted by one step inside
  * each row (0 at a row's first step).  hprev_ws: scratch fp32 [m_bound, dirs*H].
  * Out: dw_hh [dirs, 3H, H].  (Bias gradients are column sums: ttr_colsum.)  Runs ttr_gemm_tn_tf32:

@@ -37,7 +37,7 @@ _SIGNATURES = {
     "ttr_gru_recurrence_fwd_f16": [P, P, P, P, P, I32, I32, I32, P, P, P, I64, P],
     "ttr_gemm_f16_bias": [P, P, P, P, I32, P, I32, I32, P],
     "ttr_f32_to_f16": [P, P, I64, P],
-    "ttr_gru_recurrence_bwd_ws": [P, P, P, P, P, P, P, I32, I32, I32, P, P, P, I64, P],
+    "ttr_gru_recurrence_bwd_ws": [P, P, P, P, P, P, P, I32, I32, I32, P, P, P, I64, I32, P, P, P, P],
     "ttr_gru_recurrence_bwd": [P, P, P, P, P, P, P, I32, I32, I32, P, P, P],
     "ttr_gru_whh_grad": [P, P, P, I32, I32, I32, I32, P, P, I32, P],
     "ttr_proj_l2norm_fwd": [P, P, P, I32, I32, I32, I32, P, P, P],

@@ -290,7 +290,7 @@ gru_hprev_kernel(const float* __restrict__ y, const int32_t* __restrict__ offset
 int64_t gru_bwd_tc_workspace_bytes(int B, int dirs);
 int launch_gru_bwd_tc(const float* dy, const float* dh_last, const float* y, const float* saved, const float* w_hh,
                       const int32_t* order, const int32_t* offsets, int B, int dirs, float* dgi, float* dgh,
-                      void* workspace, cudaStream_t st);
+                      void* workspace, float* db_ih, float* db_hh, cudaStream_t st);
 
 }  // namespace ttr
 
@@ -305,6 +305,7 @@ extern "C" int ttr_gru_recurrence_bwd(const float* dy, const float* dh_last, con
 extern "C" int ttr_gru_recurrence_bwd_ws(const float* dy, const float* dh_last, const float* y, const float* saved,
                                          const float* w_hh, const int32_t* order, const int32_t* offsets, int B, int H,
                                          int dirs, float* dgi, float* dgh, void* workspace, int64_t workspace_bytes,
+                                         int m_bound, const int32_t* m_valid, float* db_ih, float* db_hh,
                                          void* stream) {
   using namespace ttr;
   TTR_REQUIRE(B >= 1 && H >= 1 && (dirs == 1 || dirs == 2), "ttr_gru_recurrence_bwd_ws: bad shape");
@@ -312,9 +313,14 @@ extern "C" int ttr_gru_recurrence_bwd_ws(const float* dy, const float* dh_last, 
   if (H == BH && workspace != nullptr && !(g_debug_flags & (1 | (1 << 23)))) {
     TTR_REQUIRE(workspace_bytes >= gru_bwd_tc_workspace_bytes(B, dirs), "ttr_gru_recurrence_bwd_ws: workspace of %lld B < %lld B",
                 (long long)workspace_bytes, (long long)gru_bwd_tc_workspace_bytes(B, dirs));
-    return launch_gru_bwd_tc(dy, dh_last, y, saved, w_hh, order, offsets, B, dirs, dgi, dgh, workspace, (cudaStream_t)stream);
+    return launch_gru_bwd_tc(dy, dh_last, y, saved, w_hh, order, offsets, B, dirs, dgi, dgh, workspace, db_ih, db_hh,
+                             (cudaStream_t)stream);
   }
-  return ttr_gru_recurrence_bwd(dy, dh_last, y, saved, w_hh, order, offsets, B, H, dirs, dgi, dgh, stream);
+  int rc = ttr_gru_recurrence_bwd(dy, dh_last, y, saved, w_hh, order, offsets, B, H, dirs, dgi, dgh, stream);
+  // the other kernels leave the bias gradients to the column-sum kernel (accumulating, like the fused path)
+  if (rc == TTR_OK && db_hh) rc = ttr_colsum(dgh, m_bound, m_valid, dirs * 3 * H, db_hh, 1, stream);
+  if (rc == TTR_OK && db_ih) rc = ttr_colsum(dgi, m_bound, m_valid, dirs * 3 * H, db_ih, 1, stream);
+  return rc;
 }
 
 extern "C" int ttr_gru_recurrence_bwd(const float* dy, const float* dh_last, const float* y, const float* saved,

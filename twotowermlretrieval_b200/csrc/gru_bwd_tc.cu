@@ -22,6 +22,8 @@
 //   * the elementwise phase is not tied to tensor-memory lanes, so threads are mapped (row, 4 units) with
 //     8 lanes covering a row's 128-byte segment: every global load/store of saved gates, dy, h_prev, d(gi),
 //     d(gh) and the accumulator is coalesced without shuffles.
+//   * the bias gradients (column sums of d(gi) and d(gh) over all tokens: what `ttr_colsum` would re-read
+//     12 KB per token for) are accumulated in registers on the way and added to db_ih / db_hh once per CTA.
 #include <cudaTypedefs.h>
 #include <cuda_fp16.h>
 
@@ -62,6 +64,8 @@ struct GruBwdTcArgs {
   float* dgi;             // [Mtok, dirs*3H]
   float* dgh;             // [Mtok, dirs*3H]
   float* acc;             // [clusters][2][128][256] fp32, zero on entry
+  float* db_ih;           // [dirs*3H] += column sums of d(gi)  (or null)
+  float* db_hh;           // [dirs*3H] += column sums of d(gh)  (or null)
 };
 
 namespace {
@@ -181,6 +185,11 @@ gru_bwd_tc_kernel(GruBwdTcArgs a, const __grid_constant__ CUtensorMap map_acc) {
   // elementwise phase: thread = (rows rsub + 32*it, units 4*c4 .. 4*c4+3 of the CTA's slice)
   const int rsub = tid >> 3, c4 = tid & 7;
   const int j4 = rank * BT_UN + 4 * c4;                       // first of the thread's 4 global hidden units
+  float dbs[4][4];                                            // running sums of dr, dz, dn, dn*r over rows and steps
+#pragma unroll
+  for (int g = 0; g < 4; ++g)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) dbs[g][e] = 0.f;
   float dhz[4][4];                                            // dh_t * z carried to the next step
 #pragma unroll
   for (int it = 0; it < 4; ++it)
@@ -253,6 +262,7 @@ gru_bwd_tc_kernel(GruBwdTcArgs a, const __grid_constant__ CUtensorMap map_acc) {
           dr[e] = dn[e] * ghn[e] * r[e] * (1.f - r[e]);
           dgn[e] = dn[e] * r[e];
           dhz[it][e] = dh[e] * z[e];
+          dbs[0][e] += dr[e]; dbs[1][e] += dz[e]; dbs[2][e] += dn[e]; dbs[3][e] += dgn[e];
           dgh_s[0][e] = dr[e] * BT_SCALE; dgh_s[1][e] = dz[e] * BT_SCALE; dgh_s[2][e] = dgn[e] * BT_SCALE;
         }
         float* gi = a.dgi + (size_t)tok * g_ld + dir * G3 + j4;
@@ -334,6 +344,23 @@ gru_bwd_tc_kernel(GruBwdTcArgs a, const __grid_constant__ CUtensorMap map_acc) {
 
   ptx::tc_fence_before_sync();
   __syncthreads();
+  if (a.db_ih || a.db_hh) {
+    // bias gradients: reduce the 32 row groups through shared memory (the staging area is idle now), one global add per column
+    float* red = reinterpret_cast<float*>(stg);               // [4 arrays][32 units]
+    if (tid < 4 * BT_UN) red[tid] = 0.f;
+    __syncthreads();
+#pragma unroll
+    for (int g = 0; g < 4; ++g)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) atomicAdd(&red[g * BT_UN + 4 * c4 + e], dbs[g][e]);
+    __syncthreads();
+    if (tid < 3 * BT_UN) {
+      const int g = tid / BT_UN, u = tid % BT_UN;
+      const int col = dir * G3 + g * BT_H + rank * BT_UN + u;
+      if (a.db_ih) atomicAdd(a.db_ih + col, red[g * BT_UN + u]);                       // dr, dz, dn
+      if (a.db_hh) atomicAdd(a.db_hh + col, red[(g == 2 ? 3 : g) * BT_UN + u]);        // dr, dz, dn * r
+    }
+  }
   cluster_sync_b();
   if (warp == 1) ptx::tmem_dealloc(tmem_base, BT_TMEM_COLS);
 }
@@ -344,14 +371,15 @@ int64_t gru_bwd_tc_workspace_bytes(int B, int dirs) {
 
 int launch_gru_bwd_tc(const float* dy, const float* dh_last, const float* y, const float* saved, const float* w_hh,
                       const int32_t* order, const int32_t* offsets, int B, int dirs, float* dgi, float* dgh,
-                      void* workspace, cudaStream_t st) {
+                      void* workspace, float* db_ih, float* db_hh, cudaStream_t st) {
   const int64_t ws_bytes = gru_bwd_tc_workspace_bytes(B, dirs);
   TTR_CHECK_CUDA(cudaMemsetAsync(workspace, 0, (size_t)ws_bytes, st));
   CUtensorMap map_acc;
   const int64_t rows = (int64_t)ceil_div(B, BT_ROWS) * dirs * BT_ACC_ROWS_PER_CLUSTER;
   int rc = make_rowmajor_map(&map_acc, reinterpret_cast<const float*>(workspace), rows, BT_H, BT_ROWS, false);
   if (rc != TTR_OK) return rc;
-  GruBwdTcArgs a{dy, dh_last, y, saved, w_hh, order, offsets, B, dirs, dgi, dgh, reinterpret_cast<float*>(workspace)};
+  GruBwdTcArgs a{dy, dh_last, y, saved, w_hh, order, offsets, B, dirs, dgi, dgh, reinterpret_cast<float*>(workspace),
+                 db_ih, db_hh};
   TTR_CHECK_CUDA(cudaFuncSetAttribute(gru_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BT_SMEM));
   dim3 grid(ceil_div(B, BT_ROWS) * BT_CL, dirs);
   gru_bwd_tc_kernel<<<grid, BT_THREADS, BT_SMEM, st>>>(a, map_acc);

@@ -71,7 +71,8 @@ def encoder_backward(enc, ctx: dict, d_out: torch.Tensor) -> List[Optional[torch
         ws_bytes = int(_lib.load().ttr_gru_bwd_workspace_bytes(B, H, dirs))
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev) if ws_bytes else None
         _lib.call("ttr_gru_recurrence_bwd_ws", dy, dh_last, ctx["ys"][layer], ctx["saveds"][layer], W_hh,
-                  plan.order, plan.offsets, B, H, dirs, dgi, dgh, ws, ws_bytes)
+                  plan.order, plan.offsets, B, H, dirs, dgi, dgh, ws, ws_bytes, Mb, plan.total,
+                  gview("bias_ih", layer), gview("bias_hh", layer))       # bias gradients accumulate into the zeroed views
         # weight gradients on the tensor cores (tf32, token dimension reduced with split-K); the
         # operands' rows between the valid token count and the next multiple of 32 must be zero
         layer_in = ctx["layer_ins"][layer]
@@ -81,8 +82,6 @@ def encoder_backward(enc, ctx: dict, d_out: torch.Tensor) -> List[Optional[torch
         _lib.call("ttr_gru_whh_grad", dgh, ctx["ys"][layer], plan.offsets, B, H, dirs, Mb, hprev,
                   gview("weight_hh", layer), 0)
         del hprev
-        _lib.call("ttr_colsum", dgh, Mb, plan.total, G, gview("bias_hh", layer), 0)
-        _lib.call("ttr_colsum", dgi, Mb, plan.total, G, gview("bias_ih", layer), 0)
         _lib.call("ttr_gemm_tn_tf32", dgi, G, layer_in, in_dim, gview("weight_ih", layer), in_dim, Mb, plan.total,
                   G, in_dim, 0)
         del dgh
