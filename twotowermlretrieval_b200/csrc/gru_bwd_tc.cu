@@ -196,6 +196,33 @@ gru_bwd_tc_kernel(GruBwdTcArgs a, const __grid_constant__ CUtensorMap map_acc) {
 #pragma unroll
     for (int e = 0; e < 4; ++e) dhz[it][e] = 0.f;
   float* acc_cluster = a.acc + (size_t)cid * BT_ACC_ROWS_PER_CLUSTER * BT_H;
+  // Inputs of a step that do not depend on the recurrence (saved gates, dy, h_prev) are fetched one step ahead,
+  // right after the MMAs are issued: their HBM latency hides behind the MMA, the reduce and the cluster signal
+  // instead of heading the next step's dependency chain (the step is a latency chain: with 16 clusters in flight
+  // at 1,024 rows nothing else fills the SM).
+  float4 pre[4][6];                                           // [item][r, z, n, ghn, dy, h_prev]
+  auto prefetch = [&](int s) {
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      const int row = rsub + 32 * it;
+      const int len = lens[row];
+#pragma unroll
+      for (int v = 0; v < 6; ++v) pre[it][v] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (s >= 0 && s < len) {
+        const int pos = (dir == 0) ? s : len - 1 - s;
+        const int tok = toff[row] + pos;
+        const float* sv = a.saved + ((size_t)tok * a.dirs + dir) * 4 * BT_H + j4;
+#pragma unroll
+        for (int v = 0; v < 4; ++v) pre[it][v] = __ldg(reinterpret_cast<const float4*>(sv + v * BT_H));
+        if (a.dy) pre[it][4] = __ldg(reinterpret_cast<const float4*>(a.dy + (size_t)tok * y_ld + dir * BT_H + j4));
+        if (s > 0) {
+          const int tokp = toff[row] + ((dir == 0) ? s - 1 : len - s);
+          pre[it][5] = __ldg(reinterpret_cast<const float4*>(a.y + (size_t)tokp * y_ld + dir * BT_H + j4));
+        }
+      }
+    }
+  };
+  prefetch(maxlen - 1);
   // reduce phase: warp = (TMEM lane quarter q, column half uh)
   const int q = warp & 3, uh = warp >> 2;
   const int r_in_tile = q * 32 + lane;
@@ -232,24 +259,15 @@ gru_bwd_tc_kernel(GruBwdTcArgs a, const __grid_constant__ CUtensorMap map_acc) {
           dh4.x = fmaf(av.x, 1.0f / BT_SCALE, dh4.x); dh4.y = fmaf(av.y, 1.0f / BT_SCALE, dh4.y);
           dh4.z = fmaf(av.z, 1.0f / BT_SCALE, dh4.z); dh4.w = fmaf(av.w, 1.0f / BT_SCALE, dh4.w);
         }
-        if (a.dy) {
-          const float4 v = __ldg(reinterpret_cast<const float4*>(a.dy + (size_t)tok * y_ld + dir * BT_H + j4));
+        {
+          const float4 v = pre[it][4];
           dh4.x += v.x; dh4.y += v.y; dh4.z += v.z; dh4.w += v.w;
         }
         if (s == len - 1 && a.dh_last) {
           const float4 v = __ldg(reinterpret_cast<const float4*>(a.dh_last + (size_t)rowid[row] * y_ld + dir * BT_H + j4));
           dh4.x += v.x; dh4.y += v.y; dh4.z += v.z; dh4.w += v.w;
         }
-        const float* sv = a.saved + ((size_t)tok * a.dirs + dir) * 4 * BT_H + j4;
-        const float4 r4 = __ldg(reinterpret_cast<const float4*>(sv));
-        const float4 z4 = __ldg(reinterpret_cast<const float4*>(sv + BT_H));
-        const float4 n4 = __ldg(reinterpret_cast<const float4*>(sv + 2 * BT_H));
-        const float4 g4 = __ldg(reinterpret_cast<const float4*>(sv + 3 * BT_H));
-        float4 hp = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (s > 0) {
-          const int tokp = toff[row] + ((dir == 0) ? s - 1 : len - s);
-          hp = __ldg(reinterpret_cast<const float4*>(a.y + (size_t)tokp * y_ld + dir * BT_H + j4));
-        }
+        const float4 r4 = pre[it][0], z4 = pre[it][1], n4 = pre[it][2], g4 = pre[it][3], hp = pre[it][5];
         const float dh[4] = {dh4.x, dh4.y, dh4.z, dh4.w};
         const float r[4] = {r4.x, r4.y, r4.z, r4.w}, z[4] = {z4.x, z4.y, z4.z, z4.w};
         const float n[4] = {n4.x, n4.y, n4.z, n4.w}, ghn[4] = {g4.x, g4.y, g4.z, g4.w};
@@ -308,6 +326,7 @@ gru_bwd_tc_kernel(GruBwdTcArgs a, const __grid_constant__ CUtensorMap map_acc) {
       }
       __syncwarp();
     }
+    prefetch(s - 1);                                          // next step's inputs, in flight during MMA + reduce
     ptx::mbar_wait(mma_done, par);
     ptx::tc_fence_after_sync();
 
