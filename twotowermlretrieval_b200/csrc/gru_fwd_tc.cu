@@ -75,6 +75,7 @@ struct GruTcArgs {
   float* h_last;
   float* saved;
   unsigned char* scratch;   // [clusters][chains][2][TC_A_BYTES] operand images for the multicast exchange
+  int tile_rows;            // rows per cluster: TC_TILE (two chains) or TC_ROWS (one chain; small batches)
   long long* trace;   // diagnostic: [8][256] clock64 of cluster 0 / CTA 0 at eight points of each step, or NULL
 };
 
@@ -240,7 +241,7 @@ gru_fwd_tc_kernel(GruTcArgs a) {
   const int tile = blockIdx.x / TC_CL;
   const int dir = blockIdx.y;
   const int G3 = 3 * TC_H;
-  const int s0 = tile * TC_TILE;
+  const int s0 = tile * a.tile_rows;
 
   if (tid == 0) {
     for (int c = 0; c < TC_CHAINS; ++c) {
@@ -256,7 +257,7 @@ gru_fwd_tc_kernel(GruTcArgs a) {
   }
   for (int i = tid; i < TC_TILE; i += TC_THREADS) {
     const int s = s0 + i;
-    if (s < a.B) {
+    if (s < a.B && i < a.tile_rows) {
       const int off = a.offsets[s];
       lens[i] = a.offsets[s + 1] - off;
       toff[i] = off;
@@ -458,16 +459,27 @@ gru_fwd_tc_kernel(GruTcArgs a) {
   if (warp == 1) ptx::tmem_dealloc(tmem_base, TC_TMEM_COLS);
 }
 
+// Steps are latency chains, so when every cluster of 128-row tiles is co-resident anyway (<= 15 of them) one
+// chain per cluster on twice as many SMs beats two interleaved chains per cluster.
+// More generally: the fewest rows per cluster (>= 128, <= 256, multiple of 8) that keeps the whole batch within
+// the 15 clusters of 8 a B200 holds at once; chain 1 then carries the rows beyond 128 (possibly only a few).
+static int tc_tile_rows(int B, int dirs) {
+  const int slots = 15 / dirs;                                   // cluster tiles per direction in one wave
+  const int need = ceil_div(ceil_div(B, slots), 8) * 8;
+  return need <= TC_ROWS ? TC_ROWS : (need <= TC_TILE ? need : TC_TILE);
+}
+
 int64_t gru_fwd_tc_workspace_bytes(int B, int dirs) {
-  return (int64_t)ceil_div(B, TC_TILE) * dirs * TC_CHAINS * 2 * TC_A_BYTES;
+  return (int64_t)ceil_div(B, TC_ROWS) * dirs * TC_CHAINS * 2 * TC_A_BYTES;      // sized for either tiling
 }
 
 int launch_gru_fwd_tc(const float* gi, const float* w_hh, const float* b_hh, const int32_t* order,
                       const int32_t* offsets, int B, int dirs, float* y, float* h_last, float* saved, void* workspace,
                       bool half_io, cudaStream_t st) {
+  const int tile_rows = tc_tile_rows(B, dirs);
   GruTcArgs a{gi, w_hh, b_hh, order, offsets, B, dirs, y, h_last, saved, reinterpret_cast<unsigned char*>(workspace),
-              g_score_trace};
-  dim3 grid(ceil_div(B, TC_TILE) * TC_CL, dirs);
+              tile_rows, g_score_trace};
+  dim3 grid(ceil_div(B, tile_rows) * TC_CL, dirs);
   if (half_io) {
     TTR_REQUIRE(saved == nullptr, "tcgen05 GRU with fp16 gi/y is inference-only (saved must be NULL)");
     TTR_CHECK_CUDA(cudaFuncSetAttribute(gru_fwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
