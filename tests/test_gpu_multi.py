@@ -96,6 +96,7 @@ def _worker(rank, world, port, q):
                 opt.step()
         a, b = m_dp.flat_params(), m_one.flat_params()
         out["dp_max_param_diff"] = float((a - b).abs().max())
+        out["dp_frac_off"] = float(((a - b).abs() > 1e-4).float().mean())
         out["dp_norms"] = (float(opt_dp.last_grad_norm), float(opt_one.last_grad_norm))
         torch.cuda.synchronize()
         q.put((rank, out))
@@ -118,8 +119,11 @@ def test_two_rank_sharded_search_hybrid_and_dp_training():
         r = res[rank]
         assert r["search3"] and r["search40"] and r["hybrid"], r
         assert r["peer_memory"], "symmetric-memory exchange was not active"
-        # mean-of-means over equal shards == mean over the global batch; clip + Adam identical up to fp32
-        # reduction order.  Two Adam steps at lr=1e-3 move every weight by ~1e-3 each; elements whose
-        # gradient is ~eps may differ by a few percent of that.
-        assert r["dp_max_param_diff"] < 1e-4, r
+        # mean-of-means over equal shards == mean over the global batch; clip + Adam identical up to the fp32
+        # summation order of the gradients (the copy-engine reductions of the BPTT and weight-gradient kernels add
+        # in arrival order, and the two runs tile the rows differently).  Adam's first steps move every weight by
+        # lr * sign(g): an element whose gradient is below that noise (~1e-6 of the tensor's scale) can take the
+        # other sign, so single elements may differ by up to 2 steps * 2 lr while all but a vanishing fraction agree.
+        assert r["dp_max_param_diff"] <= 4.1e-3, r
+        assert r["dp_frac_off"] < 1e-3, r
         assert abs(r["dp_norms"][0] - r["dp_norms"][1]) < 1e-3 * r["dp_norms"][1], r
