@@ -107,9 +107,9 @@ class ClockSampler:
 
 def ncu_traffic(batch: int, shard_rows: int):
     """dram__bytes_read.sum + dram__bytes_write.sum of the scoring kernel from the committed
-    `ncu --set full` capture (profiles/r1_score_topk_mma_v5_ncu_raw.csv) — only valid for the exact
+    `ncu --set full` capture (profiles/r1_score_topk_mma_v6_ncu_raw.csv) — only valid for the exact
     configuration that was captured (B=128, full corpus on one GPU); null otherwise."""
-    p = ROOT / "profiles" / "r1_score_topk_mma_v5_ncu_raw.csv"
+    p = ROOT / "profiles" / "r1_score_topk_mma_v6_ncu_raw.csv"
     if batch != 128 or shard_rows != N_DOCS or not p.exists():
         return None
     try:

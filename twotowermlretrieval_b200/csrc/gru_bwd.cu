@@ -270,13 +270,29 @@ __global__ void __launch_bounds__(256) gru_bwd_generic_kernel(GruBwdArgs a, int 
   }
 }
 
-// hprev[tok(step s)] = y[tok(step s-1)] (0 at the first step) for every direction
+// hprev[tok(step s)] = y[tok(step s-1)] (0 at the first step) for every direction.  One CTA per row, one
+// 16-byte column chunk per thread (no per-element div/mod: the first version spent 0.33 ms per call on 0.57 GB).
 __global__ void __launch_bounds__(128)
 gru_hprev_kernel(const float* __restrict__ y, const int32_t* __restrict__ offsets, int H, int dirs,
                  float* __restrict__ hprev) {
   const int s = blockIdx.x;
   const int off = offsets[s], len = offsets[s + 1] - off;
   const int ld = dirs * H;
+  if ((H & 3) == 0) {
+    const int ld4 = ld >> 2;
+    const float4* y4 = reinterpret_cast<const float4*>(y);
+    float4* h4 = reinterpret_cast<float4*>(hprev);
+    for (int c = threadIdx.x; c < ld4; c += blockDim.x) {
+      const int step = ((c << 2) / H == 0) ? -1 : 1;            // forward direction looks one token back, reverse one ahead
+      for (int t = 0; t < len; ++t) {
+        const int tp = t + step;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (tp >= 0 && tp < len) v = __ldg(y4 + (size_t)(off + tp) * ld4 + c);
+        h4[(size_t)(off + t) * ld4 + c] = v;
+      }
+    }
+    return;
+  }
   for (int i = threadIdx.x; i < len * ld; i += blockDim.x) {
     const int t = i / ld, c = i % ld;
     const int dir = c / H;
