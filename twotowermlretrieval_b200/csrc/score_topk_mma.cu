@@ -809,8 +809,14 @@ static int launch_select_merge(const float* outs, const int32_t* outi, const int
                                int64_t idx_offset, float* res_s, int64_t* res_i, cudaStream_t st) {
   const int stage_cap = (g_debug_flags & 512) ? 0 : merge_stage_cap(n_slices);   // bit 9: force the L2 re-read path
   const size_t smem = (size_t)stage_cap * 8;
-  TTR_CHECK_CUDA(cudaFuncSetAttribute(topk_select_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      MG_MAX_STAGE * 8));
+  static thread_local int attr_dev = -1;            // once per host thread and device: five driver calls per search otherwise
+  int cur_dev = 0;
+  TTR_CHECK_CUDA(cudaGetDevice(&cur_dev));
+  if (attr_dev != cur_dev) {
+    TTR_CHECK_CUDA(cudaFuncSetAttribute(topk_select_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        MG_MAX_STAGE * 8));
+    attr_dev = cur_dev;
+  }
   topk_select_merge_kernel<<<B, MG_THREADS, smem, st>>>(outs, outi, outn, n_slices, k, idx_offset, stage_cap, res_s,
                                                        res_i);
   TTR_CHECK_LAUNCH();
@@ -857,9 +863,15 @@ int launch_score_topk_mma(const float* Q, int B, const float* docs, int64_t N, i
   init_tau_kernel<<<ceil_div(nq_pad, 256), 256, 0, st>>>(tau, outn, nq_pad, counters);
   TTR_CHECK_LAUNCH();
   const size_t smem = (size_t)SM_STAGES * SM_STAGE_BYTES + SM_LIST_BYTES + SM_LISTI_BYTES + (2 * SM_STAGES + 2 * SM_NACC) * 8 + 16 + 1024;
-  TTR_CHECK_CUDA(cudaFuncSetAttribute(score_topk_mma_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  TTR_CHECK_CUDA(cudaFuncSetAttribute(score_topk_mma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  TTR_CHECK_CUDA(cudaFuncSetAttribute(score_topk_mma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  static thread_local int attr_dev = -1;
+  int cur_dev = 0;
+  TTR_CHECK_CUDA(cudaGetDevice(&cur_dev));
+  if (attr_dev != cur_dev) {
+    TTR_CHECK_CUDA(cudaFuncSetAttribute(score_topk_mma_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    TTR_CHECK_CUDA(cudaFuncSetAttribute(score_topk_mma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    TTR_CHECK_CUDA(cudaFuncSetAttribute(score_topk_mma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_dev = cur_dev;
+  }
   const FusedArgs no_fuse{nullptr, nullptr, 0};
   // Sample pass: exact top-k of the first ~38 k documents gives every query a k-th-best bound
   // (top ~0.1 %) before the full scan starts.  Without it each CTA spends its first ~250
