@@ -20,11 +20,12 @@
 //     math against the gi row segment it prefetched while the MMAs ran, results written to
 //     y / saved / h_last, and the new h values written as fp16 straight into the CTA's own slice
 //     of the A operand.
-//   * exchange: the epilogue threads also write the fp16 values into the CTA's 8 KB slice of a
-//     double-buffered global scratch image of the operand (L2-resident), and one elected thread
-//     then issues ONE cp.async.bulk ... multicast::cluster load that lands the slice in all eight
-//     CTAs' A operands and completes on each destination's mbarrier — no cluster-wide barrier in
-//     the loop and 8 KB instead of 56 KB leaving the SM per step.  (The first version pushed the
+//   * exchange: one elected thread copies the CTA's 8 KB slice from its own A operand to a
+//     double-buffered global scratch image of the operand (L2-resident) with a bulk store, waits for
+//     that store, and issues ONE cp.async.bulk ... multicast::cluster load that lands the slice in
+//     the seven peers' A operands and completes on each destination's mbarrier — no cluster-wide
+//     barrier in the loop and 8 KB instead of 56 KB leaving the SM per step.  (Writing the scratch
+//     with plain stores needed a gpu-scope fence in every epilogue thread: 2.3 k cycles per step.)  (The first version pushed the
 //     slice with shared::cta -> shared::cluster bulk copies: 15-30 B/clk per SM, the longest phase
 //     of the step, profiles/r1_gru_tc_trace_v1.txt.)  The write-after-read hazard (a peer's MMA
 //     still reading its operand) is covered by a second mbarrier that every CTA's MMA completion
@@ -104,6 +105,10 @@ __device__ __forceinline__ void bulk_g2s_multicast(uint32_t dst, const void* src
       : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+// shared::cta -> global bulk copy (bulk async-group completion)
+__device__ __forceinline__ void bulk_s2g(void* gdst, uint32_t ssrc, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(ssrc), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void mma_commit_multicast(uint64_t* bar, uint16_t mask) {
   asm volatile(
       "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
@@ -398,8 +403,9 @@ gru_fwd_tc_kernel(GruTcArgs a) {
             const int u = 8 * hf + i;
             h[u] = fmaf(zz[i], h[u] - nn[i], nn[i]);            // (1-z)*n + z*h
           }
-          // new h (fp16) -> own slice of this step's scratch image (k = 32*rank + u0 + 8*hf + i)
-          *reinterpret_cast<uint4*>(scr + (size_t)par * TC_A_BYTES + (kc0 + hf) * TC_A_LBO + row * 16) = pack8(h + 8 * hf);
+          // new h (fp16) -> own slice of the A operand (k = 32*rank + u0 + 8*hf + i); the issuing thread copies the
+          // slice to the scratch image and multicasts it to the peers
+          *reinterpret_cast<uint4*>(h_sm + (kc0 + hf) * TC_A_LBO + row * 16) = pack8(h + 8 * hf);
           if (a.saved) {
             float4* sv = reinterpret_cast<float4*>(a.saved + ((size_t)tok * a.dirs + dir) * 4 * TC_H + j0 + 8 * hf);
 #pragma unroll
@@ -415,8 +421,7 @@ gru_fwd_tc_kernel(GruTcArgs a) {
     }
     if (wg == 0 && lane == 0 && ch == 0) TC_TRACE(4);
     ptx::tc_fence_before_sync();
-    __threadfence();                      // the slice written above must be in L2 ...
-    fence_proxy_async_all();              // ... and ordered before the copy engine's (async proxy) read of it
+    ptx::fence_proxy_async_smem();        // the slice written above is read by the copy engine and by the tensor core
     ptx::named_bar_sync(1 + ch, TC_GROUP);
     if (wg == 0 && lane == 0 && ch == 0) TC_TRACE(5);
     // the exchange is issued first (below, by one thread of warp 0); the per-step outputs leave after the
@@ -433,12 +438,17 @@ gru_fwd_tc_kernel(GruTcArgs a) {
     if (wg == 0 && t + 1 < maxlen) {
       // ===== exchange: once all 8 CTAs have finished reading h_{t-1}, land the new slice in all of them =====
       if (ptx::elect_one()) {
+        // own slice: smem -> scratch image in L2 by the copy engine; its completion orders it before the multicast
+        // load below (a per-thread gpu-scope fence after plain stores cost ~2.3 k cycles of the step here)
+        const uint32_t off = (uint32_t)rank * TC_SLICE_BYTES;
+        bulk_s2g(scr + (size_t)par * TC_A_BYTES + off, h_u32 + off, TC_SLICE_BYTES);
+        ptx::bulk_commit_group();
+        ptx::bulk_wait_group<0>();
         ptx::mbar_wait(consumed, par);
         if (ch == 0) TC_TRACE(6);
-        ptx::mbar_arrive_expect_tx(h_full, TC_CL * TC_SLICE_BYTES);      // eight slices arrive here, one per CTA
-        const uint32_t off = (uint32_t)rank * TC_SLICE_BYTES;
+        ptx::mbar_arrive_expect_tx(h_full, (TC_CL - 1) * TC_SLICE_BYTES);      // seven slices arrive here, one per peer
         bulk_g2s_multicast(h_u32 + off, scr + (size_t)par * TC_A_BYTES + off, TC_SLICE_BYTES, ptx::smem_u32(h_full),
-                           (uint16_t)0xff);
+                           (uint16_t)(0xff & ~(1u << rank)));
         if (ch == 0) TC_TRACE(7);
       }
       __syncwarp();
