@@ -153,3 +153,32 @@ def test_two_rank_gloo_shard_gather_merge_equals_global_topk():
     res = [q.get(timeout=180) for _ in range(2)]
     [p.join(60) for p in procs]
     assert all(ok for _, ok, _ in res) and all(err < 1e-6 for _, _, err in res)
+
+
+def test_corpus_artifact_reader_formats_and_errors(tmp_path):
+    """`artifacts.load_corpus_artifacts` reads the reference writer's files (`backend/main.py:134-149`) without a
+    GPU: documents.pkl, document_embeddings.npy (fp32, memory-mapped), tfidf_artifacts.pkl; inconsistent
+    directories and missing files are reported like the reference's readers would (`open` -> FileNotFoundError)."""
+    import pickle
+    from sklearn.feature_extraction.text import TfidfVectorizer
+    from twotowermlretrieval_b200.artifacts import load_corpus_artifacts
+    from twotowermlretrieval_b200.data import pad_rows
+    docs = ["deep neural network layer", "vector search index", "machine learning model for text", "image and video"]
+    vec = TfidfVectorizer(stop_words="english", max_features=20000)
+    mat = vec.fit_transform(docs)
+    emb = np.arange(len(docs) * 8, dtype=np.float32).reshape(len(docs), 8)
+    with open(tmp_path / "documents.pkl", "wb") as fh:
+        pickle.dump(docs, fh)
+    np.save(tmp_path / "document_embeddings.npy", emb)
+    with open(tmp_path / "tfidf_artifacts.pkl", "wb") as fh:
+        pickle.dump({"vectorizer": vec, "matrix": mat}, fh)
+    d2, e2, v2, m2 = load_corpus_artifacts(tmp_path)
+    assert d2 == docs and np.array_equal(np.asarray(e2), emb) and e2.dtype == np.float32
+    assert (m2 != mat).nnz == 0 and v2.vocabulary_ == vec.vocabulary_
+    np.save(tmp_path / "document_embeddings.npy", emb[:3])
+    with pytest.raises(ValueError):
+        load_corpus_artifacts(tmp_path)
+    with pytest.raises(FileNotFoundError):
+        load_corpus_artifacts(tmp_path / "nope")
+    p = pad_rows([[1, 2, 3], [], [7]])
+    assert p.dtype == torch.int64 and p.tolist() == [[1, 2, 3], [0, 0, 0], [7, 0, 0]]
