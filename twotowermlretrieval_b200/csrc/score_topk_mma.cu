@@ -56,7 +56,7 @@ constexpr int SM_KEEP = 64;                             // a compaction leaves k
 constexpr int SM_LIST_BYTES = SM_CAP * SM_MQ * 4;       // score lists ([slot][thread]): 64 KB
 constexpr int SM_LISTI_BYTES = SM_CAP * SM_MQ * 2;      // id lists, uint16 CTA-local document numbers: 32 KB
 constexpr int SM_MAX_TILES_PER_CTA = 65536 / SM_ND;     // so that a local document number fits 16 bits
-constexpr int SM_SAMPLE_TOP = 8;                        // candidates a CTA publishes per query in the sample pass
+constexpr int SM_SAMPLE_TOP = 4;                        // candidates a CTA publishes per query in the sample pass
 
 __device__ __forceinline__ void atomic_max_float(float* addr, float v) {
   if (v >= 0.f) atomicMax(reinterpret_cast<int*>(addr), __float_as_int(v));
@@ -270,10 +270,12 @@ __device__ __forceinline__ float kth_largest_128(float* smem_f, const float* __r
 // no compaction) and publishes those.  The k-th best of the union over all CTAs is a valid lower
 // bound on the final k-th best (every published candidate is a real document), and it equals the
 // exact k-th best of the sample unless one CTA holds more than SM_SAMPLE_TOP of the sample's top k
-// (256 documents of ~38 k per CTA: mean 0.34 of the top 50).
+// (256-512 documents of ~38-76 k per CTA: mean 0.34 of the top 50; with 4 kept P(more) ~ 2e-4 per CTA, and
+// then the bound is merely a little looser).  Keeping 4 instead of 8 halves the bubble and the number of
+// documents that survive in SOME lane of the warp-uniform loop: 0.263 -> 0.246 ms per step on a 1.1 M shard.
 //
 // MODE 2 (one query tile, all CTAs co-resident — cooperative launch) fuses the two passes into one launch:
-// every CTA first runs its sample tiles through the register top-8 path and writes them to a fixed slot of
+// every CTA first runs its sample tiles through the register top-4 path and writes them to a fixed slot of
 // `samp` ([query][slice][8]); a grid-wide barrier; CTA q (q < B) radix-selects the k-th best of query q's
 // n_slices * 8 sample scores into tau_g[q]; a second barrier; then the main pass over ALL tiles with the seeded
 // bound.  The TMA and MMA warps simply keep running ahead into the main tiles while the barriers pass.  This
@@ -458,7 +460,7 @@ score_topk_mma_kernel(const float* __restrict__ Q, const __grid_constant__ CUten
     // microseconds, so it is refreshed every 8 tiles and consumed one refresh later.
     float tg = (q_valid && !FUSED) ? __ldcg(tau_g + q) : (q_valid ? -INFINITY : INFINITY);   // seeded by the sample pass (or -inf)
     float tg_pending = tg;
-    // one tile of the epilogue; `smp` (compile-time) selects the register top-8 path of the sample phase.  Two
+    // one tile of the epilogue; `smp` (compile-time) selects the register top-4 path of the sample phase.  Two
     // instantiations instead of a runtime flag: with the flag in the loop the main pass ran 10 % slower.
     auto tile_body = [&](const int it, auto smp_tag) {
       constexpr bool smp = decltype(smp_tag)::value;
@@ -878,7 +880,7 @@ int launch_score_topk_mma(const float* Q, int B, const float* docs, int64_t N, i
   // tiles appending and compacting almost everything it sees (3-4 k cycles per tile instead
   // of ~1.2 k; profiles/r1_score_topk_mma_v4_trace_*).  The bound is valid for any document
   // order; its tightness only matters for speed.
-  // 16 tiles per SM for big shards, 8 for small ones: since the sample epilogue keeps a register top-8
+  // 16 tiles per SM for big shards, 8 for small ones: since the sample epilogue keeps a register top-4
   // instead of lists the pass is ~35 us fixed + ~4 us per tile, and a tighter bound saves the main
   // pass more than that (measured: 8.8 M docs 8 -> 16 tiles 1.62 -> 1.56 ms; 1.1 M docs 4 -> 8 tiles
   // 0.295 -> 0.275 ms per 128-query step)
