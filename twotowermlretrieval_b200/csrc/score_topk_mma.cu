@@ -880,12 +880,14 @@ int launch_score_topk_mma(const float* Q, int B, const float* docs, int64_t N, i
   // tiles appending and compacting almost everything it sees (3-4 k cycles per tile instead
   // of ~1.2 k; profiles/r1_score_topk_mma_v4_trace_*).  The bound is valid for any document
   // order; its tightness only matters for speed.
-  // 16 tiles per SM for big shards, 8 for small ones: since the sample epilogue keeps a register top-4
-  // instead of lists the pass is ~35 us fixed + ~4 us per tile, and a tighter bound saves the main
-  // pass more than that (measured: 8.8 M docs 8 -> 16 tiles 1.62 -> 1.56 ms; 1.1 M docs 4 -> 8 tiles
-  // 0.295 -> 0.275 ms per 128-query step)
+  // Sample size: 1/20 of a CTA's tiles, between 4 and 32 per SM.  Since the sample epilogue keeps a register
+  // top-4 instead of lists the pass is ~35 us fixed + 1-2 us per tile, and a tighter bound saves the main pass more
+  // than that (measured per 128-query step: 8.8 M docs 8 -> 16 -> 32 tiles 1.62 -> 1.56 -> 1.50 ms; 1.1 M docs
+  // 4 -> 8 -> 12 tiles 0.295 -> 0.275 -> 0.244 ms with the cheaper epilogue)
   const int tiles_override = (g_debug_flags >> 12) & 63;          // bits 12-17: sample tiles per SM (experiments)
-  const int64_t n_sample = (int64_t)sm_count() * (tiles_override ? tiles_override : (N >= 4000000 ? 16 : 8)) * SM_ND;
+  const int64_t tiles_per_cta = ceil_div64(ceil_div64(N, (int64_t)SM_ND), (int64_t)sm_count());
+  const int tiles_auto = (int)std::min<int64_t>(32, std::max<int64_t>(4, tiles_per_cta / 20));
+  const int64_t n_sample = (int64_t)sm_count() * (tiles_override ? tiles_override : tiles_auto) * SM_ND;
   const int sample_tiles = (int)(n_sample / SM_ND / sm_count());
   // one query tile and one CTA per SM: sample phase, bound selection and main pass in ONE cooperative launch
   static int fused_ok = -1;                   // -1 unknown, 0 the device refused the cooperative launch once
