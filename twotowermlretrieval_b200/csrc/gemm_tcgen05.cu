@@ -18,7 +18,6 @@ namespace ttr {
 constexpr int GM = 128;            // tile rows  (UMMA M)
 constexpr int GN = 128;            // tile cols  (UMMA N)
 constexpr int GK = 32;             // fp32 elements per k-block = one 128-byte swizzle row
-constexpr int G_STAGES = 4;             // default ring depth (the kernel takes the depth as an argument)
 constexpr int G_MAX_STAGES = 6;
 constexpr int G_A_BYTES = GM * GK * 4;   // 16 KB
 constexpr int G_B_BYTES = GN * GK * 4;   // 16 KB
@@ -26,7 +25,6 @@ constexpr int G_STAGE_BYTES = G_A_BYTES + G_B_BYTES;
 constexpr int G_ACC_COLS = GN;           // fp32 accumulator columns per buffer
 constexpr int G_TMEM_COLS = 2 * G_ACC_COLS;
 constexpr int G_THREADS = 384;             // warp 0 TMA, 1 MMA, 2 TMEM alloc, 4-7 and 8-11 two epilogue groups
-constexpr int G_EPI_GROUPS = 2;            // group g drains accumulator buffer g (tiles local % 2 == g)
 constexpr int G_OUT_BYTES = GM * 32 * 4;   // staging buffer of one 128-row x 128-byte output chunk: 16 KB (x2 per group)
 constexpr int G_F16_PITCH = GN * 2 + 16;   // F16: staging row of a whole 128-column fp16 tile + 16 B (conflict-free)
 constexpr int G_F16_STAGE = GM * G_F16_PITCH;          // 34 KB per group

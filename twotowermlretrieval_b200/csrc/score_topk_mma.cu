@@ -195,6 +195,15 @@ __global__ void seed_tau_kernel(float* tau, int32_t* qcount, const float* __rest
   if (q < B && sample_i[(int64_t)q * k + (k - 1)] >= 0) tau[q] = sample_s[(int64_t)q * k + (k - 1)];
 }
 
+// Grid-barrier wait of the fused launch (all CTAs are co-resident: cooperative launch).  Bounded like the mbarrier
+// waits: a protocol bug traps (launch failure) after ~4 s instead of hanging the GPU.
+__device__ __forceinline__ void grid_wait(const unsigned int* counter, unsigned int expected) {
+  for (unsigned int spin = 0; *reinterpret_cast<const volatile unsigned int*>(counter) < expected; ++spin) {
+    __nanosleep(64);
+    if (spin > (1u << 26)) __trap();
+  }
+}
+
 // k-th largest of n floats in global memory (fused sample phase), computed by the 128 epilogue threads of a
 // CTA (named barrier 2): keys staged in `smem_f` (n <= SM_CAP * SM_MQ), MSD radix select over the
 // order-preserving 32-bit keys, 8 bits per round.  Returns -inf when fewer than k finite values exist.
@@ -323,7 +332,6 @@ score_topk_mma_kernel(const float* __restrict__ Q, const __grid_constant__ CUten
   const int slice = blockIdx.y;              // document slice
   const int q0 = qt * SM_MQ;
   const int64_t n_tiles = ceil_div64(N, (int64_t)SM_ND);
-  const int cta = slice * gridDim.x + qt;
   // this CTA's tile sequence: [FUSED: its first S tiles once more in front,] then tiles slice, slice + n_slices, ...
   const int n_mine = slice < n_tiles ? (int)((n_tiles - slice + n_slices - 1) / n_slices) : 0;
   const int S = FUSED ? fa.sample_tiles : 0;
@@ -565,7 +573,7 @@ score_topk_mma_kernel(const float* __restrict__ Q, const __grid_constant__ CUten
         ptx::named_bar_sync(2, SM_MQ);
         if (ql == 0) {
           atomicAdd(fa.counters, 1u);
-          while (*reinterpret_cast<volatile unsigned int*>(fa.counters) < (unsigned)n_slices) __nanosleep(64);
+          grid_wait(fa.counters, (unsigned)n_slices);
           __threadfence();
         }
         ptx::named_bar_sync(2, SM_MQ);
@@ -578,7 +586,7 @@ score_topk_mma_kernel(const float* __restrict__ Q, const __grid_constant__ CUten
         ptx::named_bar_sync(2, SM_MQ);
         if (ql == 0) {
           atomicAdd(fa.counters + 1, 1u);
-          while (*reinterpret_cast<volatile unsigned int*>(fa.counters + 1) < (unsigned)n_slices) __nanosleep(64);
+          grid_wait(fa.counters + 1, (unsigned)n_slices);
           __threadfence();
         }
         ptx::named_bar_sync(2, SM_MQ);
