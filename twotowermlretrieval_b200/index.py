@@ -8,6 +8,7 @@ the only exchange is an all-gather of the per-rank top-k candidate lists.
 """
 from __future__ import annotations
 
+import threading
 from dataclasses import dataclass
 from typing import Optional, Tuple
 
@@ -29,6 +30,11 @@ def _space_code(space) -> int:
 
 
 _WORKSPACES: dict = {}
+# The scorer's launches of one call share a per-device workspace (bounds, candidate lists, barrier counters) and
+# are stream-ordered; two host threads enqueueing on the same stream at once (the reference serves `/search` from
+# a thread pool, frontend/main.py:102-103) must not interleave their launches, so a call holds this lock while it
+# enqueues.  Nothing is synchronised: the lock covers microseconds of launch work.
+_SEARCH_LOCK = threading.Lock()
 
 
 def _workspace(nbytes: int, device) -> torch.Tensor:
@@ -59,13 +65,14 @@ def search_topk(Q: torch.Tensor, docs: torch.Tensor, k: int = 50, row_offset: in
     N = docs.shape[0]
     lib = _lib.load()
     nbytes = lib.ttr_score_topk_workspace_bytes(B, N, k)
-    ws = _workspace(nbytes, Q.device)
     if out is None:
         scores = torch.empty(B, k, dtype=torch.float32, device=Q.device)
         idx = torch.empty(B, k, dtype=torch.int64, device=Q.device)
     else:
         scores, idx = out
-    _lib.call("ttr_score_topk", Q, B, docs, N, D, k, int(row_offset), scores, idx, ws, ws.numel())
+    with _SEARCH_LOCK:
+        ws = _workspace(nbytes, Q.device)
+        _lib.call("ttr_score_topk", Q, B, docs, N, D, k, int(row_offset), scores, idx, ws, ws.numel())
     return scores, idx
 
 

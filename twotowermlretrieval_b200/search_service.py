@@ -21,7 +21,7 @@ import torch
 
 from . import _lib
 from .artifacts import load_index
-from .index import CsrF64
+from .index import CsrF64, _SEARCH_LOCK
 from .query_inferencer import QueryInferencer
 
 N_CANDIDATES = 50      # frontend/main.py:155
@@ -69,7 +69,8 @@ class SearchService:
         out_i = torch.empty(k, dtype=torch.int64, device=dev)
         zero_q = torch.zeros(D, dtype=torch.float32, device=dev)
         csr = self.index.tfidf
-        _lib.call("ttr_blend_topk", zero_q, 0.0, docs, N, D, csr.indptr, csr.indices, csr.data, q_idx, q_val,
+        with _SEARCH_LOCK:                  # the per-object workspace is shared by concurrent callers
+            _lib.call("ttr_blend_topk", zero_q, 0.0, docs, N, D, csr.indptr, csr.indices, csr.data, q_idx, q_val,
                   int(q_idx.numel()), 0.0, k, out_s, out_i, None, self._ws)
         res = []
         for i, s in zip(out_i.cpu().tolist(), out_s.cpu().tolist()):

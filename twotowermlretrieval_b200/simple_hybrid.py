@@ -16,7 +16,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from .index import CsrF64
+from .index import CsrF64, _SEARCH_LOCK
 from .query_inferencer import QueryInferencer
 
 
@@ -56,7 +56,8 @@ class SimpleHybridRetriever:
             self._ws = torch.empty(int(nbytes), dtype=torch.uint8, device=dev)
         out_s = torch.empty(k, dtype=torch.float64, device=dev)
         out_i = torch.empty(k, dtype=torch.int64, device=dev)
-        _lib.call("ttr_blend_topk", q, float(np.linalg.norm(q_np)), self._doc_dev, N, D, self._csr.indptr,
+        with _SEARCH_LOCK:                  # the per-object workspace is shared by concurrent callers
+            _lib.call("ttr_blend_topk", q, float(np.linalg.norm(q_np)), self._doc_dev, N, D, self._csr.indptr,
                   self._csr.indices, self._csr.data, q_idx, q_val, int(q_idx.numel()), float(self.alpha), k,
                   out_s, out_i, None, self._ws)
         idx, sc = out_i.cpu().tolist(), out_s.cpu().tolist()
