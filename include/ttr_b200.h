@@ -171,7 +171,9 @@ int ttr_positive_rank(const float* Q, const float* docs, const int64_t* target, 
  * bit10 = H=256 GRU forward on the fp32 CUDA-core cluster kernel instead of the tcgen05 one,
  * bit11/18/19 = projection-GEMM timing experiments (no stores / no staging / no weight-stationary variant),
  * bits12-17 = sample tiles per SM override, bit20 = per-CTA entry/exit times into the trace buffer,
- * bit21 = never fuse the sample pass into the main scorer launch, bit22 = always fuse it. */
+ * bit21 = never fuse the sample pass into the main scorer launch, bit22 = always fuse it,
+ * bit24 = 16-tile id segments in the tcgen05 scorer (tests cross many segment boundaries on small corpora),
+ * bit25 = scorer epilogue without the max-tree fast reject (A/B timing). */
 int ttr_debug_set_flags(int flags);
 int ttr_debug_get_flags(int* out);
 /* Diagnostic: number of 8-CTA clusters of the tcgen05 recurrence the device holds at once. */
@@ -245,6 +247,18 @@ int ttr_topk_merge_peers(const uint64_t* peer_scores_h, const uint64_t* peer_idx
                          const uint64_t* peer_tfidf_h, int P, int B, int kin, int k,
                          float* out_scores, int64_t* out_idx, double* out_tfidf, void* stream);
 
+/* The same peer-memory merge with the cross-rank barrier inside the kernel (one launch per exchange):
+ * peer_flags_h is a HOST array of P device addresses, entry p = rank p's flag array (>= P uint32 slots in
+ * symmetric memory, zeroed once before the first step).  Rank `my_rank` release-stores `step` into slot
+ * my_rank of every peer's array, waits until its own array shows `step` from every peer, then merges
+ * the peers' [B, kin] lists in place.  `step` must increase by one per call on every rank; the caller
+ * alternates two list buffers by step parity (a peer may still be reading the lists of step s-1 while
+ * this rank writes those of step s).  Replaces the all-gather named in SURVEY.md 8(e). */
+int ttr_topk_exchange_merge(const uint64_t* peer_scores_h, const uint64_t* peer_idx_h,
+                            const uint64_t* peer_tfidf_h, const uint64_t* peer_flags_h, int P, int my_rank,
+                            uint32_t step, int B, int kin, int k, float* out_scores, int64_t* out_idx,
+                            double* out_tfidf, void* stream);
+
 /* ---- K14: hybrid rerank ----------------------------------------------------------------
  * Replaces frontend/main.py:158-198: semantic = 2*cos-1 (space=0, Chroma default squared-L2)
  * or cos (space=1); tfidf = <doc TF-IDF row, query TF-IDF row> (L2-normalised CSR rows);
@@ -253,12 +267,17 @@ int ttr_topk_merge_peers(const uint64_t* peer_scores_h, const uint64_t* peer_idx
  * doc CSR: indptr int64, indices int32 (sorted per row), data fp64; query CSR likewise
  * (q_indptr int64 [B+1]).  tfidf_in: optional fp64 [B, kc] precomputed TF-IDF scores (used
  * after a cross-rank gather); if NULL they are computed from the CSR.
+ * q_sqnorm fp64 [B] / d_sqnorm fp64 [B, kc] (either may be NULL = 1.0): squared norms of the queries and of
+ * the candidates; when one is given, space 0 evaluates the general 1 - (|q|^2 + |d|^2 - 2 q.d) (a token-less
+ * query is the zero vector -> semantic = 1 - |d|^2 = 0, frontend/main.py:152-162) instead of the unit-norm
+ * shortcut 2*cos - 1.
  * Outputs (fp64 [B, top_n] each): final, semantic, tfidf; out_pos int32 [B, top_n] = position
  * in the candidate list. */
 int ttr_hybrid_rerank(const int64_t* cand_idx, const float* cand_cos, int B, int kc,
                       int64_t csr_row_offset, const int64_t* indptr, const int32_t* indices,
                       const double* data, const int64_t* q_indptr, const int32_t* q_indices,
-                      const double* q_data, const double* tfidf_in, double alpha, int space,
+                      const double* q_data, const double* tfidf_in, const double* q_sqnorm,
+                      const double* d_sqnorm, double alpha, int space,
                       int top_n, double* out_final, double* out_sem, double* out_tfidf,
                       int32_t* out_pos, void* stream);
 /* TF-IDF scores only, for candidates owned by this shard (others get 0):

@@ -38,7 +38,7 @@ def _gru_layer(packed, sd, prefix, layer: int, bi: bool):
         flat += [sd[f"{prefix}.rnn.weight_ih_l{layer}{sfx}"], sd[f"{prefix}.rnn.weight_hh_l{layer}{sfx}"],
                  sd[f"{prefix}.rnn.bias_ih_l{layer}{sfx}"], sd[f"{prefix}.rnn.bias_hh_l{layer}{sfx}"]]
     nb = int(packed.batch_sizes[0])
-    hx = torch.zeros((2 if bi else 1), nb, H, dtype=packed.data.dtype)
+    hx = torch.zeros((2 if bi else 1), nb, H, dtype=packed.data.dtype, device=packed.data.device)
     out, hn = torch._VF.gru(packed.data, packed.batch_sizes, hx, flat, True, 1, 0.0, False, bi)
     return out, hn
 

@@ -152,7 +152,7 @@ def csr_row_dot(indptr, indices, data, row: int, q_idx: np.ndarray, q_val: np.nd
 
 
 def hybrid_rerank_frontend(cand_idx, cand_cos, indptr, indices, data, q_idx, q_val,
-                           alpha: float, top_n: int = 10, space: str = "l2"):
+                           alpha: float, top_n: int = 10, space: str = "l2", q_sqnorm=None, d_sqnorm=None):
     """The `/search` rerank — reference `frontend/main.py:158-198` for ONE query.
 
     cand_idx/cand_cos: the dense top-50 (document index, cosine) in dense-rank order, i.e.
@@ -162,7 +162,16 @@ def hybrid_rerank_frontend(cand_idx, cand_cos, indptr, indices, data, q_idx, q_v
     is Python's stable `list.sort(reverse=True)` (`:197`) — ties keep dense order.
     Returns (order into the candidate list, final, semantic, tfidf), each length top_n."""
     cand_cos = np.asarray(cand_cos, dtype=np.float64)
-    sem = 2.0 * cand_cos - 1.0 if space == "l2" else cand_cos
+    if space != "l2":
+        sem = cand_cos
+    elif q_sqnorm is None and d_sqnorm is None:
+        sem = 2.0 * cand_cos - 1.0
+    else:
+        # hnswlib's squared-L2 distance for vectors that are not unit length (a token-less query is the zero
+        # vector, `query_inferencer.py:65-69`): dist = |q|^2 + |d|^2 - 2 q.d, `semantic = 1 - dist` (`:162`)
+        qn = 1.0 if q_sqnorm is None else float(q_sqnorm)
+        dn = np.ones_like(cand_cos) if d_sqnorm is None else np.asarray(d_sqnorm, np.float64)
+        sem = 1.0 - ((qn + dn) - 2.0 * cand_cos)
     if len(q_idx) > 0:
         tf = np.array([csr_row_dot(indptr, indices, data, int(r), np.asarray(q_idx), np.asarray(q_val))
                        for r in cand_idx], dtype=np.float64)

@@ -69,7 +69,7 @@ def test_binding_arity_and_types_match_header():
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
     protos = dict(re.findall(r"\b(ttr_[a-z0-9_]+)\s*\(([^)]*)\)\s*;", text))
     kinds = {ctypes.c_void_p: "p", ctypes.c_int: "i", ctypes.c_int64: "l", ctypes.c_uint64: "u", ctypes.c_float: "f",
-             ctypes.c_double: "d"}
+             ctypes.c_double: "d", ctypes.c_uint32: "w"}
     for name, sig in _lib._SIGNATURES.items():
         params = [p.strip() for p in protos[name].split(",") if p.strip() and p.strip() != "void"]
         want = []
@@ -80,6 +80,8 @@ def test_binding_arity_and_types_match_header():
                 want.append("l")
             elif p.startswith("uint64_t"):
                 want.append("u")
+            elif p.startswith("uint32_t"):
+                want.append("w")
             elif p.startswith("int"):
                 want.append("i")
             elif p.startswith("float"):

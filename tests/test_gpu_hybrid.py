@@ -148,3 +148,35 @@ def test_corpus_wide_blend_kernel_vs_numpy(cuda_device):
         own = full.cpu().numpy()
         assert (got == np.argsort(own, kind="stable")[::-1][:k]).all()
         assert (got == top).mean() > 0.9
+
+
+def test_l2_space_with_a_zero_vector_query_and_unnormalised_docs(cuda_device):
+    """a token-less query is the zero vector (query_inferencer.py:65-69); Chroma's squared-L2 distance is then
+    |d|^2 and `semantic = 1 - dist` (frontend/main.py:162) is 0 for unit documents, not 2*0 - 1.  With `q_sqnorm` /
+    `d_sqnorm` the kernel evaluates the general 1 - (|q|^2 + |d|^2 - 2 q.d); the restatement does the same."""
+    rng = np.random.default_rng(23)
+    N, F, kc = 500, 200, 50
+    indptr, indices, data = synth.make_tfidf_csr(N, n_features=F, mean_nnz=10, seed=4)
+    docs = CsrF64.from_arrays(indptr, indices, data, cuda_device)
+    qcsr, qidx, qval = _queries_csr(rng, 3, F, cuda_device)
+    D = synth.make_unit_rows(N, 256, seed=5) * np.linspace(0.5, 1.5, N, dtype=np.float32)[:, None]   # |d| != 1
+    Q = synth.make_unit_rows(3, 256, seed=6)
+    Q[0] = 0.0                                                                                       # token-less query
+    Dd, Qd = torch.tensor(D, device=cuda_device), torch.tensor(Q, device=cuda_device)
+    s, i = search_topk(Qd, Dd, kc)
+    q_sq = (Qd.double() ** 2).sum(1)
+    d_sq = (Dd[i].double() ** 2).sum(-1)
+    out = hybrid_rerank(i, s, 0.6, docs_csr=docs, q_csr=qcsr, space="l2", top_n=10, q_sqnorm=q_sq, d_sqnorm=d_sq)
+    sc, ic = s.cpu().numpy(), i.cpu().numpy()
+    for b in range(3):
+        order, fin, sem, tf = onp.hybrid_rerank_frontend(ic[b], sc[b], indptr, indices, data, qidx[b], qval[b], 0.6, top_n=10,
+                                                        space="l2", q_sqnorm=float(q_sq[b]), d_sqnorm=d_sq[b].cpu().numpy())
+        np.testing.assert_array_equal(out["pos"][b].cpu().numpy(), order)
+        np.testing.assert_allclose(out["final"][b].cpu().numpy(), fin, rtol=0, atol=1e-15)
+        np.testing.assert_allclose(out["semantic"][b].cpu().numpy(), sem, rtol=0, atol=1e-15)
+    # zero query against unit documents: dense_score == 0 exactly
+    U = torch.tensor(synth.make_unit_rows(N, 256, seed=7), device=cuda_device)
+    s, i = search_topk(Qd[:1], U, kc)
+    out = hybrid_rerank(i, s, 1.0, docs_csr=docs, q_csr=CsrF64(qcsr.indptr[:2].contiguous(), qcsr.indices, qcsr.data, 1, 0),
+                        space="l2", top_n=10, q_sqnorm=q_sq[:1])
+    assert (out["semantic"] == 0).all() and (out["final"] == 0).all()

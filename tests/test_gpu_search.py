@@ -190,3 +190,118 @@ def test_million_docs_properties(cuda_device):
         got = torch.gather(full, 1, i)
         assert torch.allclose(got, ref_s, rtol=1e-3, atol=1e-4)        # every returned doc scores like the true rank
         assert (i == ref_i).float().mean() > (0.99 if B <= 4 else 0.9)
+
+
+def _fp64_topk_on_device(Q, D, k, chunk=1 << 19):
+    """Chunked fp64 matmul + topk on the device (the reference's evaluators.py:185-186 in fp64), ties by lower index;
+    returns (scores, idx) of the exact top-k."""
+    Qd = Q.double()
+    bs = torch.empty(Q.shape[0], 0, dtype=torch.float64, device=Q.device)
+    bi = torch.empty(Q.shape[0], 0, dtype=torch.int64, device=Q.device)
+    for lo in range(0, D.shape[0], chunk):
+        sc = Qd @ D[lo:lo + chunk].double().t()
+        s, i = torch.topk(sc, min(k, sc.shape[1]), dim=1)
+        bs, bi = torch.cat([bs, s], 1), torch.cat([bi, i + lo], 1)
+        if bs.shape[1] > 8 * k:
+            o = torch.argsort(bs, dim=1, descending=True, stable=True)[:, :k]
+            bs, bi = torch.gather(bs, 1, o), torch.gather(bi, 1, o)
+    o = torch.argsort(bi, dim=1, stable=True)
+    bs, bi = torch.gather(bs, 1, o), torch.gather(bi, 1, o)
+    o = torch.argsort(bs, dim=1, descending=True, stable=True)[:, :k]
+    return torch.gather(bs, 1, o), torch.gather(bi, 1, o)
+
+
+def _check_vs_fp64(s, i, Q, D, k, rtol=1e-3, atol=1e-4):
+    """north_star tolerance: scores within 1e-3 relative (+1e-4 absolute), indices identical except at ties in it."""
+    ref_s, ref_i = _fp64_topk_on_device(Q, D, k)
+    tol = rtol * ref_s.abs() + atol
+    assert ((s.double() - ref_s).abs() <= tol).all(), float((s.double() - ref_s).abs().max())
+    assert (torch.diff(s, dim=1) <= 0).all()
+    true = (D[i.reshape(-1)].double().view(Q.shape[0], k, -1) * Q.double().unsqueeze(1)).sum(-1)
+    mism = i != ref_i
+    assert ((true - ref_s).abs() <= tol)[mism].all()          # a different document only where it ties the reference's
+    srt = torch.sort(i, dim=1).values
+    assert (srt[:, 1:] != srt[:, :-1]).all(), "duplicate indices"
+    return float(mism.float().mean())
+
+
+@pytest.mark.parametrize("B,n_check", [(128, 128), (256, 256), (4096, 256)])
+def test_headline_corpus_8p8M_docs(cuda_device, B, n_check):
+    """The bench shapes themselves: N = 8,841,823 (MS MARCO passage count) at B = 128 (two-pass path, 1,867 tiles per
+    CTA), B = 256 (two query tiles, 3,734 tiles per CTA = two id segments) and B = 4096 (32 query tiles, 4 slices,
+    34 segments), checked against chunked fp64 on the device (every 16th query at B = 4096)."""
+    N = 8_841_823
+    gen = torch.Generator(device=cuda_device).manual_seed(3)
+    D = torch.empty(N, 256, device=cuda_device)
+    for lo in range(0, N, 1 << 20):
+        hi = min(N, lo + (1 << 20))
+        D[lo:hi] = torch.nn.functional.normalize(torch.randn(hi - lo, 256, device=cuda_device, generator=gen), dim=1)
+    Q = torch.nn.functional.normalize(torch.randn(B, 256, device=cuda_device, generator=gen), dim=1)
+    s, i = search_topk(Q, D, 50)
+    sel = torch.arange(0, B, B // n_check, device=cuda_device)
+    frac = _check_vs_fp64(s[sel], i[sel], Q[sel], D, 50)
+    assert frac < 0.1, frac
+    s2, i2 = search_topk(Q, D, 50)                              # repeatable
+    assert torch.equal(i, i2) and torch.equal(s, s2)
+
+
+@pytest.mark.parametrize("B,N", [(128, 300_000), (256, 300_000), (300, 150_000), (1024, 100_000), (40, 70_001)])
+def test_id_segments_and_fast_reject(cuda_device, B, N):
+    """A CTA numbers its candidates with 16 bits inside a segment and publishes its list at every segment boundary;
+    debug bit 24 shrinks the segments to 16 tiles so a small corpus crosses dozens of boundaries (the production
+    length is 2,048 tiles: B >= 256 on the full corpus).  Exact, so: identical to the default segmentation, to the
+    two-pass path, and to the epilogue without the max-tree fast reject (bit 25)."""
+    from twotowermlretrieval_b200 import _lib
+    D = torch.tensor(synth.make_unit_rows(N, 256, seed=70 + B), device=cuda_device)
+    D[N // 2:N // 2 + 300] = D[100:400]                       # exact ties across slices and segments
+    Q = torch.tensor(synth.make_unit_rows(B, 256, seed=80 + B), device=cuda_device)
+    s_a, i_a = search_topk(Q, D, 50)
+    for flags in (1 << 24, (1 << 24) | (1 << 21), 1 << 25, (1 << 24) | (1 << 25), 1 << 21):
+        _lib.call_nostream("ttr_debug_set_flags", flags)
+        try:
+            s_b, i_b = search_topk(Q, D, 50)
+        finally:
+            _lib.call_nostream("ttr_debug_set_flags", 0)
+        assert torch.equal(s_a, s_b) and torch.equal(i_a, i_b), f"flags {flags:#x}"
+    _check_vs_fp64(s_a[:16], i_a[:16], Q[:16], D, 50)
+
+
+def test_adversarial_order_across_segments(cuda_device):
+    """Ascending scores (every document beats the running bound -> constant compaction) with 16-tile segments."""
+    from twotowermlretrieval_b200 import _lib
+    rng = np.random.default_rng(2)
+    Q = synth.make_unit_rows(130, 256, seed=6)
+    N = 40000
+    D = rng.standard_normal((N, 256)).astype(np.float32) * 0.01
+    D += np.linspace(-1, 1, N, dtype=np.float32)[:, None] * Q[0]
+    Qd, Dd = torch.tensor(Q, device=cuda_device), torch.tensor(D, device=cuda_device)
+    _lib.call_nostream("ttr_debug_set_flags", 1 << 24)
+    try:
+        s, i = search_topk(Qd, Dd, 50)
+    finally:
+        _lib.call_nostream("ttr_debug_set_flags", 0)
+    _check_vs_fp64(s[:8], i[:8], Qd[:8], Dd, 50)
+
+
+def test_concurrent_streams_do_not_share_scratch(cuda_device):
+    """re-entrant per CUDA stream — two streams search at the same time with their own workspaces."""
+    D = torch.tensor(synth.make_unit_rows(400_000, 256, seed=91), device=cuda_device)
+    Qs = [torch.tensor(synth.make_unit_rows(100, 256, seed=92 + j), device=cuda_device) for j in range(2)]
+    want = [search_topk(q, D, 50) for q in Qs]
+    torch.cuda.synchronize()
+    streams = [torch.cuda.Stream(device=cuda_device) for _ in range(2)]
+    got = [None, None]
+    for rep in range(5):
+        for j, st in enumerate(streams):
+            with torch.cuda.stream(st):
+                got[j] = search_topk(Qs[j], D, 50)
+        torch.cuda.synchronize()
+        for j in range(2):
+            assert torch.equal(got[j][1], want[j][1]) and torch.equal(got[j][0], want[j][0])
+
+
+def test_k_outside_kernel_range_is_a_clear_error(cuda_device):
+    D = torch.tensor(synth.make_unit_rows(1000, 256, seed=1), device=cuda_device)
+    Q = torch.tensor(synth.make_unit_rows(2, 256, seed=2), device=cuda_device)
+    with pytest.raises(ValueError, match="outside"):
+        search_topk(Q, D, 65)

@@ -205,3 +205,55 @@ def test_dropout_train_mode_replays_through_oracle(cuda_device):
     with torch.no_grad():
         ref = torch_path.encoder_forward(sd, "doc_encoder", x.cpu(), cfg, dropout_masks=[padded])
     assert torch.allclose(out.cpu(), ref, atol=2e-4)
+
+
+def test_config1_one_epoch_loss_curve_matches_reference_loop(cuda_device, tmp_path):
+    """BASELINE configs[0]: ONE EPOCH (157 steps, batch 64) over 10,000 synthetic triplet strings at
+    backend/config.json dims (DROPOUT 0) through `PretrainedTokenizer` -> `TripletDataset`/`collate_fn` ->
+    `TwoTowerTrainer.train_step` on the GPU, against the curve the UNMODIFIED reference loop
+    (`backend/main.py:244-259`: reference model / tokenizer / dataset / collate, clip_grad_norm_(1.0), Adam 5e-5)
+    produced on CPU (`oracle/make_golden_config1.py` -> tests/golden/config1_epoch.npz).
+    Bounds: per-step loss within 1e-3; pre-clip gradient norm within 2 %; the 157-step parameter movement
+    (final - initial, strided subsample of every tensor) within 15 % in relative L2 — Adam moves each weight by
+    ~lr * sign(g) per step, so elements whose gradient is near the fp32/tf32 noise floor may step the other way."""
+    import pickle
+    from oracle.make_golden_config1 import SUBSAMPLE, config1_inputs
+    from twotowermlretrieval_b200.data import TripletDataset, collate_fn
+    from twotowermlretrieval_b200.tokenizer import PretrainedTokenizer
+    g = load_golden("config1_epoch")
+    cfg, words, triplets, perm, sd = config1_inputs()
+    p = tmp_path / "word_to_idx.pkl"
+    with open(p, "wb") as f:
+        pickle.dump({w: i for i, w in enumerate(words)}, f)
+    tok = PretrainedTokenizer(str(p))
+    assert tok.vocab_size() == cfg["VOCAB_SIZE"]
+    m = model_from_numpy(cfg, sd, cuda_device).train()
+    trainer = TrainerFactory.create_trainer(cfg, m, cuda_device, fused=True, clip_max_norm=1.0)
+    ds = TripletDataset(triplets, tok)
+    n_steps = int(g["n_steps"])
+    losses, norms = [], []
+    for i in range(n_steps):
+        batch = collate_fn([ds[int(j)] for j in perm[i * 64:(i + 1) * 64]])
+        loss, _, _, _ = trainer.train_step(*batch)
+        losses.append(loss)
+        norms.append(trainer.optimizer.last_grad_norm.clone())
+    losses = torch.stack(losses).cpu().numpy().astype(np.float64)
+    norms = torch.cat(norms).cpu().numpy().astype(np.float64)
+    dl = np.abs(losses - g["losses"])
+    dn = np.abs(norms - g["grad_norms"]) / g["grad_norms"]
+    print(f"config 1: max |loss - ref| {dl.max():.2e} (mean loss {losses.mean():.5f} vs {g['losses'].mean():.5f}), "
+          f"max grad-norm rel err {dn.max():.2e}")
+    assert dl.max() < 1e-3, (int(dl.argmax()), dl.max())
+    assert abs(losses.mean() - g["losses"].mean()) < 2e-4
+    assert dn.max() < 2e-2, (int(dn.argmax()), dn.max())
+    worst = 0.0
+    for k, v in m.state_dict().items():
+        if f"d::{k}" not in g:
+            continue
+        stride = 1 if v.numel() < 4096 else SUBSAMPLE
+        move = (v.reshape(-1).double().cpu().numpy() - sd[k].reshape(-1).astype(np.float64))[::stride]
+        ref = g[f"d::{k}"].astype(np.float64)
+        rel = np.linalg.norm(move - ref) / max(np.linalg.norm(ref), 1e-12)
+        worst = max(worst, rel)
+        assert rel < 0.15, (k, rel)
+    print(f"config 1: worst relative L2 error of the 157-step parameter movement {worst:.3f}")

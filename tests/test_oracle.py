@@ -184,3 +184,25 @@ def test_adam_and_clip_match_torch():
         assert abs(tn - float(tot)) < 1e-4
         p, m, v = onp.adam_step(p, gc.astype(np.float64), m, v, step, 5e-5)
         np.testing.assert_allclose(p, t.detach().numpy(), rtol=1e-5, atol=1e-7)
+
+
+def test_config1_fixture_first_steps_match_the_torch_restatement():
+    """tests/golden/config1_epoch.npz was produced by the unmodified reference loop (oracle/make_golden_config1.py);
+    the functional restatement `oracle.torch_path.train_step` reproduces its first two steps on the same batches."""
+    import torch
+    from oracle import torch_path
+    from oracle.make_golden_config1 import config1_inputs
+    from twotowermlretrieval_b200.data import pad_rows
+    g = load_golden("config1_epoch")
+    assert int(g["n_steps"]) == 157 and len(g["losses"]) == 157 and np.isfinite(g["losses"]).all()
+    cfg, words, triplets, perm, sd = config1_inputs()
+    w2i = {w: i for i, w in enumerate(words)}
+    enc = lambda s: [w2i[t] for t in s.split()]
+    sdt = torch_path.to_torch_state(sd, requires_grad=True)
+    st = {}
+    for i in range(2):
+        rows = [triplets[int(j)] for j in perm[i * 64:(i + 1) * 64]]
+        q, p, n = (pad_rows([enc(r[c]) for r in rows]) for c in range(3))
+        loss, gn = torch_path.train_step(sdt, st, cfg, q, p, n)
+        assert abs(loss - g["losses"][i]) < 2e-5, (i, loss, g["losses"][i])
+        assert abs(gn - g["grad_norms"][i]) < 1e-3 * g["grad_norms"][i]

@@ -50,10 +50,11 @@ _SIGNATURES = {
     "ttr_score_topk": [P, I32, P, I64, I32, I32, I64, P, P, P, I64, P],
     "ttr_topk_merge": [P, P, I32, I32, I32, I32, P, P, P],
     "ttr_topk_merge_peers": [P, P, P, I32, I32, I32, I32, P, P, P, P],
+    "ttr_topk_exchange_merge": [P, P, P, P, I32, I32, ctypes.c_uint32, I32, I32, I32, P, P, P, P],
     "ttr_positive_rank": [P, P, P, I32, I64, I32, P, P, P],
     "ttr_dropout": [P, I64, F32, ctypes.c_uint64, P, P, P],
     "ttr_blend_topk": [P, F32, P, I64, I32, P, P, P, P, P, I32, F64, I32, P, P, P, P, P],
-    "ttr_hybrid_rerank": [P, P, I32, I32, I64, P, P, P, P, P, P, P, F64, I32, I32, P, P, P, P, P],
+    "ttr_hybrid_rerank": [P, P, I32, I32, I64, P, P, P, P, P, P, P, P, P, F64, I32, I32, P, P, P, P, P],
     "ttr_tfidf_candidates": [P, I32, I32, I64, I64, P, P, P, P, P, P, P, P],
 }
 
@@ -104,15 +105,36 @@ def ptr(t):
     return t.data_ptr()
 
 
-def stream_ptr() -> int:
-    return torch.cuda.current_stream().cuda_stream
+def stream_ptr(device=None) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def _owning_device(args):
+    """Device of the CUDA tensor arguments of one call (None when there is none); raises when
+    they live on different devices — the library launches on ONE device and stream."""
+    dev = None
+    for a in args:
+        if isinstance(a, torch.Tensor) and a.is_cuda:
+            if dev is None:
+                dev = a.device
+            elif a.device != dev:
+                raise TTRError(f"CUDA tensor arguments on different devices ({dev} and {a.device})")
+    return dev
 
 
 def call(name: str, *args):
-    """Invoke `name`; tensors are passed by address, the current CUDA stream is appended."""
+    """Invoke `name`; tensors are passed by address.  The launch happens on the device that owns the
+    tensor arguments (not the thread's current device) and on torch's current stream OF THAT DEVICE,
+    which is appended as the last argument."""
     lib = load()
+    dev = _owning_device(args)
     conv = [ptr(a) if isinstance(a, torch.Tensor) else a for a in args]
-    rc = getattr(lib, name)(*conv, stream_ptr())
+    fn = getattr(lib, name)
+    if dev is None or dev.index == torch.cuda.current_device():
+        rc = fn(*conv, stream_ptr())
+    else:
+        with torch.cuda.device(dev):
+            rc = fn(*conv, stream_ptr(dev))
     if rc != 0:
         raise TTRError(f"{name} failed ({rc}): {lib.ttr_last_error().decode()}")
 
@@ -127,11 +149,14 @@ def call_nostream(name: str, *args):
 _SM_COUNT = {}
 
 
-def sm_count() -> int:
-    dev = torch.cuda.current_device()
+def sm_count(device=None) -> int:
+    dev = torch.cuda.current_device() if device is None else torch.device(device).index
+    if dev is None:
+        dev = torch.cuda.current_device()
     if dev not in _SM_COUNT:
         out = ctypes.c_int(0)
-        call_nostream("ttr_sm_count", ctypes.byref(out))
+        with torch.cuda.device(dev):
+            call_nostream("ttr_sm_count", ctypes.byref(out))
         _SM_COUNT[dev] = out.value
     return _SM_COUNT[dev]
 

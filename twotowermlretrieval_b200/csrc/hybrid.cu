@@ -53,7 +53,8 @@ hybrid_rerank_kernel(const int64_t* __restrict__ cand_idx, const float* __restri
                      int64_t row_offset, const int64_t* __restrict__ indptr,
                      const int32_t* __restrict__ indices, const double* __restrict__ data,
                      const int64_t* __restrict__ q_indptr, const int32_t* __restrict__ q_indices,
-                     const double* __restrict__ q_data, const double* __restrict__ tfidf_in, double alpha,
+                     const double* __restrict__ q_data, const double* __restrict__ tfidf_in,
+                     const double* __restrict__ q_sqnorm, const double* __restrict__ d_sqnorm, double alpha,
                      int space, int top_n, double* __restrict__ out_final, double* __restrict__ out_sem,
                      double* __restrict__ out_tfidf, int32_t* __restrict__ out_pos) {
   __shared__ double fin[128];
@@ -62,7 +63,17 @@ hybrid_rerank_kernel(const int64_t* __restrict__ cand_idx, const float* __restri
   const bool valid = j < kc && cand_idx[(int64_t)q * kc + j] >= 0;
   if (valid) {
     const double c = (double)cand_cos[(int64_t)q * kc + j];
-    sem = space == 0 ? __dadd_rn(__dmul_rn(2.0, c), -1.0) : c;
+    if (space != 0) {
+      sem = c;
+    } else if (q_sqnorm == nullptr && d_sqnorm == nullptr) {
+      sem = __dadd_rn(__dmul_rn(2.0, c), -1.0);                    // unit vectors: 1 - |q - d|^2 = 2 cos - 1
+    } else {
+      // general squared-L2 distance of Chroma's default space: 1 - (|q|^2 + |d|^2 - 2 q.d); a token-less query is the
+      // zero vector (query_inferencer.py:65-69) -> dist = |d|^2, an un-normalised model has |d| != 1
+      const double qn = q_sqnorm ? q_sqnorm[q] : 1.0;
+      const double dn = d_sqnorm ? d_sqnorm[(int64_t)q * kc + j] : 1.0;
+      sem = __dadd_rn(1.0, -__dadd_rn(__dadd_rn(qn, dn), -__dmul_rn(2.0, c)));
+    }
     if (tfidf_in) {
       tf = tfidf_in[(int64_t)q * kc + j];
     } else {
@@ -112,7 +123,8 @@ extern "C" int ttr_tfidf_candidates(const int64_t* cand_idx, int B, int kc, int6
 extern "C" int ttr_hybrid_rerank(const int64_t* cand_idx, const float* cand_cos, int B, int kc,
                                  int64_t csr_row_offset, const int64_t* indptr, const int32_t* indices,
                                  const double* data, const int64_t* q_indptr, const int32_t* q_indices,
-                                 const double* q_data, const double* tfidf_in, double alpha, int space,
+                                 const double* q_data, const double* tfidf_in, const double* q_sqnorm,
+                                 const double* d_sqnorm, double alpha, int space,
                                  int top_n, double* out_final, double* out_sem, double* out_tfidf,
                                  int32_t* out_pos, void* stream) {
   using namespace ttr;
@@ -122,7 +134,7 @@ extern "C" int ttr_hybrid_rerank(const int64_t* cand_idx, const float* cand_cos,
               "ttr_hybrid_rerank: need either tfidf_in or the CSR operands");
   hybrid_rerank_kernel<<<B, 128, 0, (cudaStream_t)stream>>>(cand_idx, cand_cos, kc, csr_row_offset, indptr,
                                                            indices, data, q_indptr, q_indices, q_data,
-                                                           tfidf_in, alpha, space, top_n, out_final, out_sem,
+                                                           tfidf_in, q_sqnorm, d_sqnorm, alpha, space, top_n, out_final, out_sem,
                                                            out_tfidf, out_pos);
   TTR_CHECK_LAUNCH();
   return TTR_OK;

@@ -311,9 +311,8 @@ struct PeerLists {
   const double* t[MAX_PEERS];
 };
 
-__global__ void __launch_bounds__(SC_THREADS)
-topk_merge_peers_kernel(PeerLists pl, int P, int kin, int k, float* __restrict__ out_s, int64_t* __restrict__ out_i,
-                        double* __restrict__ out_t) {
+__device__ __forceinline__ void merge_peers_body(const PeerLists& pl, int P, int kin, int k, float* __restrict__ out_s,
+                                                 int64_t* __restrict__ out_i, double* __restrict__ out_t) {
   __shared__ float buf_s[SC_WARPS][TOPK_CAP];
   __shared__ int32_t buf_i[SC_WARPS][TOPK_CAP];
   __shared__ int cnts[SC_WARPS];
@@ -331,8 +330,8 @@ topk_merge_peers_kernel(PeerLists pl, int P, int kin, int k, float* __restrict__
     int32_t src = IDX_PAD;
     if (t < total) {
       const int p = t / kin, j = t % kin;
-      if (pl.i[p][(int64_t)q * kin + j] >= 0) {
-        s = pl.s[p][(int64_t)q * kin + j];
+      if (__ldcg(pl.i[p] + (int64_t)q * kin + j) >= 0) {
+        s = __ldcg(pl.s[p] + (int64_t)q * kin + j);
         src = t;
       }
     }
@@ -368,9 +367,45 @@ topk_merge_peers_kernel(PeerLists pl, int P, int kin, int k, float* __restrict__
     const bool valid = src != IDX_PAD;
     const int p = valid ? src / kin : 0, e = valid ? src % kin : 0;
     out_s[(int64_t)q * k + j] = mrg_s[j];
-    out_i[(int64_t)q * k + j] = valid ? pl.i[p][(int64_t)q * kin + e] : (int64_t)-1;
-    if (out_t) out_t[(int64_t)q * k + j] = (valid && pl.t[p]) ? pl.t[p][(int64_t)q * kin + e] : 0.0;
+    out_i[(int64_t)q * k + j] = valid ? __ldcg(pl.i[p] + (int64_t)q * kin + e) : (int64_t)-1;
+    if (out_t) out_t[(int64_t)q * k + j] = (valid && pl.t[p]) ? __ldcg(pl.t[p] + (int64_t)q * kin + e) : 0.0;
   }
+}
+
+__global__ void __launch_bounds__(SC_THREADS)
+topk_merge_peers_kernel(PeerLists pl, int P, int kin, int k, float* __restrict__ out_s, int64_t* __restrict__ out_i,
+                        double* __restrict__ out_t) {
+  merge_peers_body(pl, P, kin, k, out_s, out_i, out_t);
+}
+
+// The same merge with the cross-rank barrier INSIDE the kernel: rank r tells every peer "my lists of step s are
+// complete" by a release store of s into slot r of the peer's flag array (symmetric memory), then waits until its own
+// array shows step s from every peer (acquire loads), then reads the peers' lists in place.  The lists were written by
+// the previous kernels of this stream, i.e. they are complete in this GPU's memory before the flag leaves it.  One
+// launch replaces the host-side symmetric-memory barrier (a kernel of its own) + the merge launch: ~25 us per search
+// step at 8 GPUs (profiles/r2_*).  Every CTA signals (idempotent: the value is the step number) so that progress does
+// not depend on which CTA is scheduled first; waits are bounded (trap instead of a hung GPU).
+struct PeerFlags {
+  uint32_t* f[MAX_PEERS];
+};
+
+__global__ void __launch_bounds__(SC_THREADS)
+topk_exchange_merge_kernel(PeerLists pl, PeerFlags pf, int P, int my_rank, uint32_t step, int kin, int k,
+                           float* __restrict__ out_s, int64_t* __restrict__ out_i, double* __restrict__ out_t) {
+  if (threadIdx.x < P) {
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(pf.f[threadIdx.x] + my_rank), "r"(step) : "memory");
+    const uint32_t* mine = pf.f[my_rank] + threadIdx.x;
+    for (uint32_t spin = 0;; ++spin) {
+      uint32_t v;
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mine) : "memory");
+      if ((int32_t)(v - step) >= 0) break;
+      __nanosleep(32);
+      if (spin > (1u << 27)) __trap();
+    }
+  }
+  __syncthreads();
+  merge_peers_body(pl, P, kin, k, out_s, out_i, out_t);
 }
 
 static int simt_grid_parts() { return sm_count(); }
@@ -466,6 +501,28 @@ extern "C" int ttr_topk_merge_peers(const uint64_t* peer_scores_h, const uint64_
     pl.t[p] = (p < P && peer_tfidf_h) ? reinterpret_cast<const double*>(peer_tfidf_h[p]) : nullptr;
   }
   topk_merge_peers_kernel<<<B, SC_THREADS, 0, (cudaStream_t)stream>>>(pl, P, kin, k, out_scores, out_idx, out_tfidf);
+  TTR_CHECK_LAUNCH();
+  return TTR_OK;
+}
+
+extern "C" int ttr_topk_exchange_merge(const uint64_t* peer_scores_h, const uint64_t* peer_idx_h,
+                                       const uint64_t* peer_tfidf_h, const uint64_t* peer_flags_h, int P, int my_rank,
+                                       uint32_t step, int B, int kin, int k, float* out_scores, int64_t* out_idx,
+                                       double* out_tfidf, void* stream) {
+  using namespace ttr;
+  TTR_REQUIRE(k >= 1 && k <= TOPK_KMAX, "ttr_topk_exchange_merge: k=%d outside [1, %d]", k, TOPK_KMAX);
+  TTR_REQUIRE(P >= 1 && P <= MAX_PEERS && B >= 1 && kin >= 1, "ttr_topk_exchange_merge: bad shape (P=%d)", P);
+  TTR_REQUIRE(my_rank >= 0 && my_rank < P, "ttr_topk_exchange_merge: rank %d outside [0, %d)", my_rank, P);
+  PeerLists pl;
+  PeerFlags pf;
+  for (int p = 0; p < MAX_PEERS; ++p) {
+    pl.s[p] = p < P ? reinterpret_cast<const float*>(peer_scores_h[p]) : nullptr;
+    pl.i[p] = p < P ? reinterpret_cast<const int64_t*>(peer_idx_h[p]) : nullptr;
+    pl.t[p] = (p < P && peer_tfidf_h) ? reinterpret_cast<const double*>(peer_tfidf_h[p]) : nullptr;
+    pf.f[p] = p < P ? reinterpret_cast<uint32_t*>(peer_flags_h[p]) : nullptr;
+  }
+  topk_exchange_merge_kernel<<<B, SC_THREADS, 0, (cudaStream_t)stream>>>(pl, pf, P, my_rank, step, kin, k, out_scores,
+                                                                       out_idx, out_tfidf);
   TTR_CHECK_LAUNCH();
   return TTR_OK;
 }

@@ -301,7 +301,7 @@ __global__ void __launch_bounds__(SM_THREADS, 1)
 score_topk_mma_kernel(const float* __restrict__ Q, const __grid_constant__ CUtensorMap map_d, int B, int64_t N,
                       int k, int n_slices, float* __restrict__ tau_g, float* __restrict__ out_s,
                       int32_t* __restrict__ out_i, int32_t* __restrict__ out_n, long long* __restrict__ trace,
-                      int dbg, FusedArgs fa) {
+                      int dbg, FusedArgs fa, int seg_tiles, int cap) {
   constexpr bool SAMPLE = MODE == 1;
   constexpr bool FUSED = MODE == 2;
   extern __shared__ unsigned char smem_raw[];
@@ -464,6 +464,7 @@ score_topk_mma_kernel(const float* __restrict__ Q, const __grid_constant__ CUten
     bool strict = false;
     int cnt = 0;
     int it = 0;
+    int seg_base = 0;                          // first main-pass tile of the current id segment (see `publish`)
     // Global lower bound on the k-th best.  An L2 read under a saturated memory system costs
     // microseconds, so it is refreshed every 8 tiles and consumed one refresh later.
     float tg = (q_valid && !FUSED) ? __ldcg(tau_g + q) : (q_valid ? -INFINITY : INFINITY);   // seeded by the sample pass (or -inf)
@@ -511,14 +512,30 @@ score_topk_mma_kernel(const float* __restrict__ Q, const __grid_constant__ CUten
       // one threshold, one compare per score: "strictly above tau" == ">= next float above tau"
       const float thr = smp ? key2f(f2key(top_s[SM_SAMPLE_TOP - 1]) + 1u)         // must beat the weakest kept score
                             : fmaxf(tg, strict ? key2f(f2key(tau) + 1u) : tau);
+      // Fast reject: the maximum of the thread's 32 scores (a 5-level FMNMX tree, ~35 issue slots) against the
+      // threshold, one vote per warp.  After the sample pass seeded the bounds only ~1 tile in 4 holds a survivor
+      // for ANY of a warp's 32 queries (r2 traces: the per-score mask build + OR-reduce + compaction vote below
+      // cost ~610 of the epilogue's ~1100 cycles per tile whether or not anything survived).
+      const bool tail = d0 + 32 > N;          // documents >= N are zero-filled by TMA and must not count
+      bool skip = false;
+      if (!(dbg & (1 << 25))) {
+        float m16[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) m16[j] = fmaxf(sc32[2 * j], sc32[2 * j + 1]);
+#pragma unroll
+        for (int w = 8; w > 0; w >>= 1)
+#pragma unroll
+          for (int j = 0; j < w; ++j) m16[j] = fmaxf(m16[j], m16[j + w]);
+        skip = !tail && !__any_sync(0xffffffffu, m16[0] >= thr);
+      }
+      if (!skip) {
       // Branch-free filter -> per-lane bit mask of surviving documents.  (A short-circuit
       // condition compiles to a branch per score: ~45 cycles of resolve latency each with one
       // warp per scheduler, 1300-1600 cycles per tile; profiles/r1_score_topk_mma_v4_trace_*.)
       uint32_t mask = 0;
 #pragma unroll
       for (int j = 0; j < 32; ++j) mask |= (sc32[j] >= thr ? 1u : 0u) << j;
-      // the tail tile: documents >= N are zero-filled by TMA and must not count
-      if (d0 + 32 > N) mask &= (N - d0 >= 32) ? 0xffffffffu : ((1u << (int)(N - d0)) - 1u);
+      if (tail) mask &= (N - d0 >= 32) ? 0xffffffffu : ((1u << (int)(N - d0)) - 1u);
       // Visit only the documents that survive in SOME lane (warp-uniform loop over the OR of
       // the lane masks, usually 0-2 bits): traversing 32 conditional regions costs ~1500 cycles
       // per tile even when nothing is appended (profiles/r1_score_topk_mma_v4_trace_*).
@@ -551,7 +568,7 @@ score_topk_mma_kernel(const float* __restrict__ Q, const __grid_constant__ CUten
           }
         } else if ((mask >> j) & 1u) {   // cnt <= SM_CAP - SM_ND before the tile, so 32 free slots exist
           ls[cnt * SM_MQ] = scj;
-          li[cnt * SM_MQ] = (uint16_t)((it - S) * SM_ND + j);
+          li[cnt * SM_MQ] = (uint16_t)((it - S - seg_base) * SM_ND + j);
           ++cnt;
         }
       }
@@ -561,40 +578,79 @@ score_topk_mma_kernel(const float* __restrict__ Q, const __grid_constant__ CUten
         cnt = thread_compact(ls, li, cnt, k, tau, strict);
         if (q_valid && cnt >= k) atomic_max_float(tau_g + q, tau);
       }
+      }
       if (qw == 0) SM_TRACE(7, it);
+    };
+    // Publish the list: at most SM_KEEP candidates at or above the global bound go to the per-query
+    // global scratch (ids become global document numbers), then the list restarts empty.  Called at the
+    // end, and every `seg_tiles` main-pass tiles in between: a list entry numbers its document with 16
+    // bits relative to the segment start, so a CTA may scan any number of tiles (one wave of CTAs for
+    // every query-tile count, instead of n_tiles / 2048 slices in several waves).  tau / strict stay
+    // valid across the reset: the k documents that justified them have been published.
+    auto publish = [&]() {
+      __syncwarp();
+      if (__any_sync(0xffffffffu, cnt > SM_KEEP)) cnt = thread_compact(ls, li, cnt, k, tau, strict);
+      if (q_valid) {
+        const float tgf = __ldcg(tau_g + q);
+        int n_keep = 0;
+        for (int e = 0; e < SM_KEEP; ++e) n_keep += (e < cnt && ls[e * SM_MQ] >= tgf) ? 1 : 0;
+        size_t ob = (size_t)q * (size_t)cap + (size_t)atomicAdd(out_n + q, n_keep);
+        for (int e = 0; e < SM_KEEP; ++e)
+          if (e < cnt && ls[e * SM_MQ] >= tgf) {
+            const int lid = li[e * SM_MQ];                     // local -> global: tile = slice + main_tile * n_slices
+            out_s[ob] = ls[e * SM_MQ];
+            out_i[ob] = (int32_t)(((int64_t)slice + (int64_t)(seg_base + (lid >> 5)) * n_slices) * SM_ND + (lid & 31));
+            ++ob;
+          }
+      }
+      cnt = 0;
+    };
+    auto main_tiles = [&]() {
+      for (; it < n_seq; ++it) {
+        if (it - S - seg_base >= seg_tiles) {   // warp-uniform
+          publish();
+          seg_base += seg_tiles;
+        }
+        tile_body(it, std::false_type{});
+      }
     };
     if (FUSED) {
       for (it = 0; it < S; ++it) tile_body(it, std::true_type{});
-        // ---- end of the sample phase: publish, grid barrier, CTA q selects query q's bound, grid barrier ----
-        float* mine = fa.samp + ((size_t)ql * n_slices + slice) * SM_SAMPLE_TOP;
+      // ---- end of the sample phase: publish, grid barrier, the CTAs select the queries' bounds, grid barrier ----
+      const unsigned n_ctas = gridDim.x * gridDim.y;
+      float* mine = fa.samp + ((size_t)(q0 + ql) * n_slices + slice) * SM_SAMPLE_TOP;
 #pragma unroll
-        for (int e = 0; e < SM_SAMPLE_TOP; ++e) mine[e] = (q_valid && top_i[e] >= 0) ? top_s[e] : -INFINITY;
+      for (int e = 0; e < SM_SAMPLE_TOP; ++e) mine[e] = (q_valid && top_i[e] >= 0) ? top_s[e] : -INFINITY;
+      __threadfence();
+      ptx::named_bar_sync(2, SM_MQ);
+      if (ql == 0) {
+        atomicAdd(fa.counters, 1u);
+        grid_wait(fa.counters, n_ctas);
         __threadfence();
+      }
+      ptx::named_bar_sync(2, SM_MQ);
+      // CTA c selects the bounds of queries c, c + n_ctas, ... (one query per CTA when B <= #CTAs)
+      for (int qq = slice * (int)gridDim.x + qt; qq < B; qq += (int)n_ctas) {
+        const float kth = kth_largest_128(list_s, fa.samp + (size_t)qq * n_slices * SM_SAMPLE_TOP,
+                                          n_slices * SM_SAMPLE_TOP, k, ql);
+        if (ql == 0) tau_g[qq] = kth;
         ptx::named_bar_sync(2, SM_MQ);
-        if (ql == 0) {
-          atomicAdd(fa.counters, 1u);
-          grid_wait(fa.counters, (unsigned)n_slices);
-          __threadfence();
-        }
-        ptx::named_bar_sync(2, SM_MQ);
-        if (slice < B) {
-          const float kth = kth_largest_128(list_s, fa.samp + (size_t)slice * n_slices * SM_SAMPLE_TOP,
-                                            n_slices * SM_SAMPLE_TOP, k, ql);
-          if (ql == 0) tau_g[slice] = kth;
-          __threadfence();
-        }
-        ptx::named_bar_sync(2, SM_MQ);
-        if (ql == 0) {
-          atomicAdd(fa.counters + 1, 1u);
-          grid_wait(fa.counters + 1, (unsigned)n_slices);
-          __threadfence();
-        }
-        ptx::named_bar_sync(2, SM_MQ);
-        tg = q_valid ? __ldcg(tau_g + q) : INFINITY;
-        tg_pending = tg;
-      for (; it < n_seq; ++it) tile_body(it, std::false_type{});
+      }
+      __threadfence();
+      ptx::named_bar_sync(2, SM_MQ);
+      if (ql == 0) {
+        atomicAdd(fa.counters + 1, 1u);
+        grid_wait(fa.counters + 1, n_ctas);
+        __threadfence();
+      }
+      ptx::named_bar_sync(2, SM_MQ);
+      tg = q_valid ? __ldcg(tau_g + q) : INFINITY;
+      tg_pending = tg;
+      main_tiles();
+    } else if (SAMPLE) {
+      for (it = 0; it < n_seq; ++it) tile_body(it, std::true_type{});
     } else {
-      for (it = 0; it < n_seq; ++it) tile_body(it, std::integral_constant<bool, SAMPLE>{});
+      main_tiles();
     }
     if (threadIdx.x == 128) SM_MARK(2);      // last tile filtered
     if (SAMPLE) {
@@ -602,28 +658,13 @@ score_topk_mma_kernel(const float* __restrict__ Q, const __grid_constant__ CUten
         int n_keep = 0;
 #pragma unroll
         for (int e = 0; e < SM_SAMPLE_TOP; ++e) n_keep += top_i[e] >= 0 ? 1 : 0;
-        size_t ob = (size_t)q * ((size_t)n_slices * SM_KEEP) + (size_t)atomicAdd(out_n + q, n_keep);
+        size_t ob = (size_t)q * (size_t)cap + (size_t)atomicAdd(out_n + q, n_keep);
 #pragma unroll
         for (int e = 0; e < SM_SAMPLE_TOP; ++e)
           if (top_i[e] >= 0) { out_s[ob] = top_s[e]; out_i[ob] = top_i[e]; ++ob; }
       }
     } else {
-    // final: leave at most SM_KEEP candidates, publish scores + count (ids stay in the scratch)
-    __syncwarp();
-    if (__any_sync(0xffffffffu, cnt > SM_KEEP)) cnt = thread_compact(ls, li, cnt, k, tau, strict);
-    if (q_valid) {
-      const float tgf = __ldcg(tau_g + q);
-      int n_keep = 0;
-      for (int e = 0; e < SM_KEEP; ++e) n_keep += (e < cnt && ls[e * SM_MQ] >= tgf) ? 1 : 0;
-      size_t ob = (size_t)q * ((size_t)n_slices * SM_KEEP) + (size_t)atomicAdd(out_n + q, n_keep);
-      for (int e = 0; e < SM_KEEP; ++e)
-        if (e < cnt && ls[e * SM_MQ] >= tgf) {
-          const int lid = li[e * SM_MQ];                     // local -> global: tile = slice + it * n_slices
-          out_s[ob] = ls[e * SM_MQ];
-          out_i[ob] = (int32_t)(((int64_t)slice + (int64_t)(lid >> 5) * n_slices) * SM_ND + (lid & 31));
-          ++ob;
-        }
-    }
+      publish();
     }
   }
 
@@ -780,11 +821,11 @@ __device__ __forceinline__ void select_merge_body(uint64_t* keys, const float* c
 
 __global__ void __launch_bounds__(MG_THREADS)
 topk_select_merge_kernel(const float* __restrict__ out_s, const int32_t* __restrict__ out_i,
-                         const int32_t* __restrict__ out_n, int n_slices, int k, int64_t idx_offset, int stage_cap,
+                         const int32_t* __restrict__ out_n, int cap_i, int k, int64_t idx_offset, int stage_cap,
                          float* __restrict__ res_s, int64_t* __restrict__ res_i) {
   extern __shared__ uint64_t mg_keys[];
   const int q = blockIdx.x;
-  const size_t cap = (size_t)n_slices * SM_KEEP;
+  const size_t cap = (size_t)cap_i;
   const int total = out_n[q];
   const float* cs = out_s + (size_t)q * cap;
   const int32_t* ci = out_i + (size_t)q * cap;
@@ -809,15 +850,12 @@ topk_select_merge_kernel(const float* __restrict__ out_s, const int32_t* __restr
   }
 }
 
-// stage capacity (keys) for a given slice count; bytes = 8 * capacity
-static int merge_stage_cap(int n_slices) {
-  const int64_t cap = (int64_t)n_slices * SM_KEEP;
-  return (int)std::min<int64_t>(cap, MG_MAX_STAGE);
-}
+// stage capacity (keys) for a given per-query candidate capacity; bytes = 8 * capacity
+static int merge_stage_cap(int cap) { return std::min(cap, MG_MAX_STAGE); }
 
-static int launch_select_merge(const float* outs, const int32_t* outi, const int32_t* outn, int B, int n_slices, int k,
+static int launch_select_merge(const float* outs, const int32_t* outi, const int32_t* outn, int B, int cap, int k,
                                int64_t idx_offset, float* res_s, int64_t* res_i, cudaStream_t st) {
-  const int stage_cap = (g_debug_flags & 512) ? 0 : merge_stage_cap(n_slices);   // bit 9: force the L2 re-read path
+  const int stage_cap = (g_debug_flags & 512) ? 0 : merge_stage_cap(cap);   // bit 9: force the L2 re-read path
   const size_t smem = (size_t)stage_cap * 8;
   static thread_local int attr_dev = -1;            // once per host thread and device: five driver calls per search otherwise
   int cur_dev = 0;
@@ -827,14 +865,14 @@ static int launch_select_merge(const float* outs, const int32_t* outi, const int
                                         MG_MAX_STAGE * 8));
     attr_dev = cur_dev;
   }
-  topk_select_merge_kernel<<<B, MG_THREADS, smem, st>>>(outs, outi, outn, n_slices, k, idx_offset, stage_cap, res_s,
-                                                       res_i);
+  topk_select_merge_kernel<<<B, MG_THREADS, smem, st>>>(outs, outi, outn, cap, k, idx_offset, stage_cap, res_s, res_i);
   TTR_CHECK_LAUNCH();
   return TTR_OK;
 }
 
 struct MmaPlan {
   int n_qt, n_slices, n_ctas;
+  int seg_tiles, n_segs, cap;       // id-segment length (tiles), segments per CTA, candidate slots per query
   int64_t tau_off, outs_off, outi_off, outn_off, samp_off, cnt_off, total;
 };
 
@@ -843,18 +881,21 @@ MmaPlan mma_plan(int B, int64_t N) {
   p.n_qt = ceil_div(B, SM_MQ);
   const int sms = sm_count();
   p.n_slices = std::max(1, sms / p.n_qt);      // one wave: n_qt * n_slices <= #SMs (1 CTA per SM)
-  // a CTA numbers its documents with 16 bits: at most 65536 documents (2048 tiles) per slice
-  const int64_t n_tiles = ceil_div64(N, (int64_t)SM_ND);
-  p.n_slices = (int)std::max<int64_t>(p.n_slices, ceil_div64(n_tiles, (int64_t)SM_MAX_TILES_PER_CTA));
   p.n_ctas = p.n_qt * p.n_slices;
+  // a list entry numbers its document with 16 bits inside a segment of <= 2048 tiles; the CTA publishes its list at
+  // every segment boundary (debug bit 24: 16-tile segments, so small test corpora cross many boundaries)
+  p.seg_tiles = (g_debug_flags & (1 << 24)) ? 16 : SM_MAX_TILES_PER_CTA;
+  const int64_t n_tiles = ceil_div64(N, (int64_t)SM_ND);
+  p.n_segs = (int)std::max<int64_t>(1, ceil_div64(ceil_div64(n_tiles, (int64_t)p.n_slices), (int64_t)p.seg_tiles));
+  p.cap = p.n_slices * p.n_segs * SM_KEEP;
   auto align = [](int64_t v) { return (v + 255) / 256 * 256; };
   const int64_t bp = (int64_t)p.n_qt * SM_MQ;
   p.tau_off = 0;
   p.outs_off = align(bp * 4);
-  p.outi_off = align(p.outs_off + (int64_t)p.n_ctas * SM_KEEP * SM_MQ * 4);
-  p.outn_off = align(p.outi_off + (int64_t)p.n_ctas * SM_KEEP * SM_MQ * 4);
-  p.samp_off = align(p.outn_off + bp * 4);                                   // fused mode: [128][n_slices][8] fp32
-  p.cnt_off = align(p.samp_off + (int64_t)SM_MQ * p.n_slices * SM_SAMPLE_TOP * 4);
+  p.outi_off = align(p.outs_off + bp * p.cap * 4);
+  p.outn_off = align(p.outi_off + bp * p.cap * 4);
+  p.samp_off = align(p.outn_off + bp * 4);                                   // fused mode: [queries][n_slices][4] fp32
+  p.cnt_off = align(p.samp_off + bp * p.n_slices * SM_SAMPLE_TOP * 4);
   p.total = align(p.cnt_off + 16);
   return p;
 }
@@ -896,42 +937,46 @@ int launch_score_topk_mma(const float* Q, int B, const float* docs, int64_t N, i
   const int64_t tiles_per_cta = ceil_div64(ceil_div64(N, (int64_t)SM_ND), (int64_t)sm_count());
   const int tiles_auto = (int)std::min<int64_t>(32, std::max<int64_t>(4, tiles_per_cta / 20));
   const int64_t n_sample = (int64_t)sm_count() * (tiles_override ? tiles_override : tiles_auto) * SM_ND;
-  const int sample_tiles = (int)(n_sample / SM_ND / sm_count());
-  // one query tile and one CTA per SM: sample phase, bound selection and main pass in ONE cooperative launch
-  static int fused_ok = -1;                   // -1 unknown, 0 the device refused the cooperative launch once
+  // The sample publishes SM_SAMPLE_TOP scores per (CTA, query): with few slices (many query tiles) the union holds
+  // fewer than ~3k values and its k-th best is no bound worth a pass -> large batches start unseeded (their CTAs
+  // scan >= 8 k tiles each, the ~250-tile transient is noise there).
+  const bool sample_useful = p.n_slices * SM_SAMPLE_TOP >= 3 * k;
+  // all CTAs co-resident (one wave): sample phase, bound selection and main pass in ONE cooperative launch
+  static int fused_ok[64];                    // per device: 0 unknown, 1 works, -1 the device refused the cooperative launch
   // (measured: 0.263 vs 0.274 ms per 128-query step on a 1.1 M-document shard, no difference on 8.8 M documents,
   // where the two-pass path stays the default; debug bit 22 forces the fused launch there too)
   const bool fuse_size = N < 4000000 || (g_debug_flags & (1 << 22));
-  if (N >= 16 * n_sample && !(g_debug_flags & (256 | (1 << 21))) && p.n_qt == 1 && p.n_slices <= sm_count() && B <= p.n_slices &&
-      fused_ok != 0 && fuse_size) {
+  if (N >= 16 * n_sample && sample_useful && !(g_debug_flags & (256 | (1 << 21))) && p.n_ctas <= sm_count() &&
+      fused_ok[cur_dev & 63] >= 0 && fuse_size) {
     CUtensorMap map_f;
     int rcf = make_tf32_rowmajor_map(&map_f, docs, N, SM_DIM, SM_ND);
     if (rcf != TTR_OK) return rcf;
-    FusedArgs fa{samp, counters, sample_tiles};
+    // every query sees the same number of sample documents whatever the slice count
+    FusedArgs fa{samp, counters, (int)ceil_div64(n_sample / SM_ND, (int64_t)p.n_slices)};
     long long* tr = g_score_trace;
     int dbgv = g_debug_flags;
-    int n_sl = p.n_slices;
+    int n_sl = p.n_slices, seg = p.seg_tiles, cap = p.cap;
     void* args[] = {(void*)&Q, (void*)&map_f, (void*)&B, (void*)&N, (void*)&k, (void*)&n_sl, (void*)&tau, (void*)&outs,
-                    (void*)&outi, (void*)&outn, (void*)&tr, (void*)&dbgv, (void*)&fa};
-    cudaError_t ce = cudaLaunchCooperativeKernel((const void*)score_topk_mma_kernel<2>, dim3(1, p.n_slices), dim3(SM_THREADS),
-                                                 args, smem, st);
+                    (void*)&outi, (void*)&outn, (void*)&tr, (void*)&dbgv, (void*)&fa, (void*)&seg, (void*)&cap};
+    cudaError_t ce = cudaLaunchCooperativeKernel((const void*)score_topk_mma_kernel<2>, dim3(p.n_qt, p.n_slices),
+                                                 dim3(SM_THREADS), args, smem, st);
     if (ce == cudaSuccess) {
-      fused_ok = 1;
-      return launch_select_merge(outs, outi, outn, B, p.n_slices, k, row_offset, out_scores, out_idx, st);
+      fused_ok[cur_dev & 63] = 1;
+      return launch_select_merge(outs, outi, outn, B, p.cap, k, row_offset, out_scores, out_idx, st);
     }
     (void)cudaGetLastError();                 // not co-resident on this device/partition: use the two-pass path
-    fused_ok = 0;
+    fused_ok[cur_dev & 63] = -1;
   }
-  if (N >= 16 * n_sample && !(g_debug_flags & 256)) {
+  if (N >= 16 * n_sample && sample_useful && !(g_debug_flags & 256)) {
     MmaPlan ps = mma_plan(B, n_sample);
     CUtensorMap map_s;
     int rc = make_tf32_rowmajor_map(&map_s, docs, n_sample, SM_DIM, SM_ND);
     if (rc != TTR_OK) return rc;
     dim3 gs(ps.n_qt, ps.n_slices);
     score_topk_mma_kernel<1><<<gs, SM_THREADS, smem, st>>>(Q, map_s, B, n_sample, k, ps.n_slices, tau, outs, outi,
-                                                          outn, nullptr, g_debug_flags, no_fuse);
+                                                          outn, nullptr, g_debug_flags, no_fuse, ps.seg_tiles, ps.cap);
     TTR_CHECK_LAUNCH();
-    rc = launch_select_merge(outs, outi, outn, B, ps.n_slices, k, 0, out_scores, out_idx, st);
+    rc = launch_select_merge(outs, outi, outn, B, ps.cap, k, 0, out_scores, out_idx, st);
     if (rc != TTR_OK) return rc;
     seed_tau_kernel<<<ceil_div(nq_pad, 256), 256, 0, st>>>(tau, outn, out_scores, out_idx, B, nq_pad, k);
     TTR_CHECK_LAUNCH();
@@ -941,9 +986,9 @@ int launch_score_topk_mma(const float* Q, int B, const float* docs, int64_t N, i
   if (rc != TTR_OK) return rc;
   dim3 grid(p.n_qt, p.n_slices);
   score_topk_mma_kernel<0><<<grid, SM_THREADS, smem, st>>>(Q, map_d, B, N, k, p.n_slices, tau, outs, outi, outn,
-                                                           g_score_trace, g_debug_flags, no_fuse);
+                                                           g_score_trace, g_debug_flags, no_fuse, p.seg_tiles, p.cap);
   TTR_CHECK_LAUNCH();
-  return launch_select_merge(outs, outi, outn, B, p.n_slices, k, row_offset, out_scores, out_idx, st);
+  return launch_select_merge(outs, outi, outn, B, p.cap, k, row_offset, out_scores, out_idx, st);
 }
 
 int64_t score_topk_mma_workspace_bytes(int B, int64_t N) { return mma_plan(B, N).total; }

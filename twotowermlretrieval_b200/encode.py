@@ -3,18 +3,20 @@
 
 The reference encodes 64 strings at a time and copies every batch back to the host.  Here
 rows are sorted by length on the host (the host tokenised them, so lengths are free),
-packed into large padded batches of similar length, staged through pinned memory with
-asynchronous H2D copies, encoded with the zero-length check disabled (no device->host sync
-per batch), and written straight into the resident output matrix in caller order.
+packed into large padded batches of similar length, staged through TWO persistent pinned
+buffers with asynchronous H2D copies on a side stream (the host fills batch i+1 while the
+copy engine moves batch i and the SMs encode batch i-1), encoded with the zero-length check
+disabled (no device->host sync per batch), and written straight into the resident output
+matrix — e.g. a rank's shard of the search index — in caller order.
 """
 from __future__ import annotations
 
-from typing import List, Optional, Sequence
+from typing import Optional, Sequence, Tuple, Union
 
 import numpy as np
 import torch
 
-from . import _lib
+Ragged = Tuple[np.ndarray, np.ndarray]      # (flat int64 token ids, int64 lengths)
 
 
 def plan_batches(lengths: np.ndarray, max_tokens: int, max_rows: int):
@@ -32,50 +34,93 @@ def plan_batches(lengths: np.ndarray, max_tokens: int, max_rows: int):
     return order, bounds
 
 
-def encode_rows(encoder, rows: Sequence[Sequence[int]], device, out: Optional[torch.Tensor] = None,
-                out_offset: int = 0, max_tokens: int = 262144, max_rows: int = 16384) -> torch.Tensor:
-    """Encode tokenised rows with `encoder` (an RNNEncoder) -> fp32 [len(rows), H] on `device`
-    (rows of `out[out_offset:]` if given).  Raises RuntimeError for empty rows like the
-    reference's pack_padded_sequence (quirk #2)."""
+def to_ragged(rows: Union[Ragged, Sequence[Sequence[int]]]) -> Ragged:
+    """List of token-id lists (what `PretrainedTokenizer.encode` returns per string) -> one flat
+    int64 array + lengths; a (flat, lengths) pair passes through."""
+    if isinstance(rows, tuple) and len(rows) == 2 and isinstance(rows[0], np.ndarray):
+        return np.ascontiguousarray(rows[0], dtype=np.int64), np.asarray(rows[1], dtype=np.int64)
     n = len(rows)
+    lengths = np.fromiter((len(r) for r in rows), dtype=np.int64, count=n)
+    flat = np.empty(int(lengths.sum()), dtype=np.int64)
+    o = 0
+    for r in rows:
+        m = len(r)
+        flat[o:o + m] = r
+        o += m
+    return flat, lengths
+
+
+class _Staging:
+    """One pinned (ids, out-row index) buffer pair and the event of the last H2D copy out of it."""
+
+    def __init__(self, max_tokens: int, max_rows: int):
+        self.ids = torch.empty(max_tokens, dtype=torch.int64).pin_memory()
+        self.idx = torch.empty(max_rows, dtype=torch.int64).pin_memory()
+        self.ids_np, self.idx_np = self.ids.numpy(), self.idx.numpy()
+        self.copied: Optional[torch.cuda.Event] = None
+
+
+def encode_rows(encoder, rows: Union[Ragged, Sequence[Sequence[int]]], device, out: Optional[torch.Tensor] = None,
+                out_offset: int = 0, max_tokens: int = 262144, max_rows: int = 16384) -> torch.Tensor:
+    """Encode tokenised rows with `encoder` (an RNNEncoder) -> fp32 [n, H] on `device`
+    (rows `out[out_offset : out_offset + n]` if `out` is given).  `rows` is a list of id lists or a
+    (flat ids, lengths) pair.  Raises RuntimeError for empty rows like the reference's
+    pack_padded_sequence (quirk #2)."""
+    flat, lengths = to_ragged(rows)
+    n = len(lengths)
     H = encoder.hidden_dim
     if out is None:
         out = torch.empty(n, H, dtype=torch.float32, device=device)
         out_offset = 0
     if n == 0:
         return out
-    lengths = np.fromiter((len(r) for r in rows), dtype=np.int64, count=n)
+    starts = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum(lengths, out=starts[1:])
     # quirk #1: the effective length is the count of non-zero ids; rows are passed through untouched,
     # the device plan recounts.  Only the all-zero / empty case is an error.
-    nnz = np.fromiter((sum(1 for t in r if t != 0) for r in rows), dtype=np.int64, count=n)
-    if (nnz <= 0).any():
+    nnz = np.add.reduceat((flat != 0).astype(np.int64), starts[:-1][lengths > 0]) if flat.size else np.zeros(0, np.int64)
+    if (lengths <= 0).any() or (nnz <= 0).any():
         from .model import _ZERO_LEN_MSG
         raise RuntimeError(_ZERO_LEN_MSG)
     order, bounds = plan_batches(lengths, max_tokens, max_rows)
+    max_tok = max((hi - lo) * int(lengths[order[lo]]) for lo, hi in bounds)
+    max_row = max(hi - lo for lo, hi in bounds)
+    stage = [_Staging(max_tok, max_row) for _ in range(2)]
     was_strict, was_training = encoder.strict_lengths, encoder.training
     encoder.strict_lengths = False
     encoder.eval()
-    copy_stream = torch.cuda.Stream(device=device)
+    dev = torch.device(device)
+    main = torch.cuda.current_stream(dev)
+    copy_stream = torch.cuda.Stream(device=dev)
     try:
         with torch.no_grad():
-            staged = None
             for bi, (lo, hi) in enumerate(bounds):
+                st = stage[bi & 1]
+                if st.copied is not None:
+                    st.copied.synchronize()              # the copy engine has read this buffer (two batches ago)
                 idx = order[lo:hi]
-                T = int(lengths[idx[0]])
-                host = torch.zeros(hi - lo, T, dtype=torch.int64).pin_memory()
-                hv = host.numpy()
-                for r, src in enumerate(idx):
-                    row = rows[src]
-                    hv[r, :len(row)] = row
+                R, T = hi - lo, int(lengths[idx[0]])
+                # vectorised fill: padded [R, T] view of the pinned buffer <- ragged rows
+                hv = st.ids_np[:R * T].reshape(R, T)
+                ln = lengths[idx]
+                pos = np.arange(T, dtype=np.int64)[None, :]
+                mask = pos < ln[:, None]
+                hv[...] = 0
+                hv[mask] = flat[(starts[idx][:, None] + pos)[mask]]
+                st.idx_np[:R] = idx + out_offset
                 with torch.cuda.stream(copy_stream):
-                    dev_ids = host.to(device, non_blocking=True)
-                    dev_idx = torch.from_numpy(idx.astype(np.int64) + out_offset).pin_memory().to(device, non_blocking=True)
-                torch.cuda.current_stream(device).wait_stream(copy_stream)
+                    dev_ids = st.ids[:R * T].view(R, T).to(dev, non_blocking=True)
+                    dev_idx = st.idx[:R].to(dev, non_blocking=True)
+                    st.copied = torch.cuda.Event()
+                    st.copied.record(copy_stream)
+                main.wait_stream(copy_stream)
+                encoder._token_bound = int(nnz[idx].sum())      # rows of the packed per-token matrices (<= R * T)
                 emb = encoder(dev_ids)
                 out.index_copy_(0, dev_idx, emb)
-                dev_ids.record_stream(torch.cuda.current_stream(device))
-                dev_idx.record_stream(torch.cuda.current_stream(device))
+                dev_ids.record_stream(main)
+                dev_idx.record_stream(main)
     finally:
+        encoder._token_bound = None
         encoder.strict_lengths = was_strict
         encoder.train(was_training)
     return out

@@ -17,6 +17,7 @@ import torch
 
 from . import _lib
 
+KMAX = 64          # TOPK_KMAX of the kernels (csrc/topk_common.cuh)
 SPACE_L2 = 0       # Chroma default: semantic = 1 - ||q-d||^2 = 2cos - 1 (frontend/main.py:162)
 SPACE_COSINE = 1   # semantic = cos
 
@@ -29,20 +30,29 @@ def _space_code(space) -> int:
     raise ValueError(f"unknown space {space!r} (use 'l2' or 'cosine')")
 
 
+class _Workspace:
+    """Scratch of the scorer (bounds, candidate lists, grid-barrier counters) for ONE (device, stream): launches on
+    different streams never share scratch, so concurrent searches are safe (re-entrant per CUDA stream).
+    `lock` only keeps two host threads that enqueue on the SAME stream (the reference serves `/search` from a thread
+    pool, frontend/main.py:102-103) from interleaving the launches of their calls; nothing is synchronised."""
+    __slots__ = ("buf", "lock")
+
+    def __init__(self):
+        self.buf = None
+        self.lock = threading.Lock()
+
+
 _WORKSPACES: dict = {}
-# The scorer's launches of one call share a per-device workspace (bounds, candidate lists, barrier counters) and
-# are stream-ordered; two host threads enqueueing on the same stream at once (the reference serves `/search` from
-# a thread pool, frontend/main.py:102-103) must not interleave their launches, so a call holds this lock while it
-# enqueues.  Nothing is synchronised: the lock covers microseconds of launch work.
-_SEARCH_LOCK = threading.Lock()
+_WS_GUARD = threading.Lock()
 
 
-def _workspace(nbytes: int, device) -> torch.Tensor:
-    key = (device.index if device.index is not None else torch.cuda.current_device())
+def _workspace(device, kind: str = "score") -> _Workspace:
+    dev = device.index if device.index is not None else torch.cuda.current_device()
+    key = (kind, dev, torch.cuda.current_stream(dev).cuda_stream)
     ws = _WORKSPACES.get(key)
-    if ws is None or ws.numel() < nbytes:
-        ws = torch.empty(int(nbytes), dtype=torch.uint8, device=device)
-        _WORKSPACES[key] = ws
+    if ws is None:
+        with _WS_GUARD:
+            ws = _WORKSPACES.setdefault(key, _Workspace())
     return ws
 
 
@@ -56,6 +66,9 @@ def search_topk(Q: torch.Tensor, docs: torch.Tensor, k: int = 50, row_offset: in
     candidate sets would raise in torch; here missing slots carry -inf / -1)."""
     _lib.require_cuda(Q, "search_topk(Q)")
     _lib.require_cuda(docs, "search_topk(docs)")
+    if not 1 <= k <= KMAX:
+        raise ValueError(f"search_topk: k={k} outside [1, {KMAX}] (the fused kernels keep at most {KMAX} "
+                         "candidates per query; the reference's own call sites use k <= 50)")
     if Q.dim() == 1:
         Q = Q.unsqueeze(0)
     Q = Q.contiguous().float()
@@ -70,10 +83,31 @@ def search_topk(Q: torch.Tensor, docs: torch.Tensor, k: int = 50, row_offset: in
         idx = torch.empty(B, k, dtype=torch.int64, device=Q.device)
     else:
         scores, idx = out
-    with _SEARCH_LOCK:
-        ws = _workspace(nbytes, Q.device)
-        _lib.call("ttr_score_topk", Q, B, docs, N, D, k, int(row_offset), scores, idx, ws, ws.numel())
+    ws = _workspace(Q.device)
+    with ws.lock:
+        if ws.buf is None or ws.buf.numel() < nbytes:
+            ws.buf = torch.empty(int(nbytes), dtype=torch.uint8, device=Q.device)
+        _lib.call("ttr_score_topk", Q, B, docs, N, D, k, int(row_offset), scores, idx, ws.buf, ws.buf.numel())
     return scores, idx
+
+
+def blend_topk(q: torch.Tensor, q_norm: float, docs: torch.Tensor, csr: "CsrF64", q_idx: torch.Tensor,
+               q_val: torch.Tensor, alpha: float, k: int):
+    """Corpus-wide alpha*dense_cos + (1-alpha)*tfidf_cos and its top-k in one pass (`ttr_blend_topk`):
+    `SimpleHybridRetriever.search` (backend/simple_hybrid.py:45-66) and, with alpha = 0, the keyword branch of
+    `/search` (frontend/main.py:119-147).  Returns (scores fp64 [k] descending, local row ids int64 [k])."""
+    dev = docs.device
+    N, D = docs.shape
+    nbytes = int(_lib.load().ttr_blend_topk_workspace_bytes(k))
+    out_s = torch.empty(k, dtype=torch.float64, device=dev)
+    out_i = torch.empty(k, dtype=torch.int64, device=dev)
+    ws = _workspace(dev, kind="blend")
+    with ws.lock:
+        if ws.buf is None or ws.buf.numel() < nbytes:
+            ws.buf = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        _lib.call("ttr_blend_topk", q, float(q_norm), docs, N, D, csr.indptr, csr.indices, csr.data, q_idx, q_val,
+                  int(q_idx.numel()), float(alpha), k, out_s, out_i, None, ws.buf)
+    return out_s, out_i
 
 
 def topk_merge(cand_scores: torch.Tensor, cand_idx: torch.Tensor, k: int) -> Tuple[torch.Tensor, torch.Tensor]:
@@ -119,10 +153,12 @@ class CsrF64:
                       self.data[base:end].contiguous(), hi - lo, self.row_offset + lo)
 
 
-def tfidf_candidates(cand_idx: torch.Tensor, docs_csr: CsrF64, q_csr: CsrF64) -> torch.Tensor:
+def tfidf_candidates(cand_idx: torch.Tensor, docs_csr: CsrF64, q_csr: CsrF64,
+                     out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """TF-IDF cosine of every candidate this shard owns (0 elsewhere): fp64 [B, kc]."""
     B, kc = cand_idx.shape
-    out = torch.empty(B, kc, dtype=torch.float64, device=cand_idx.device)
+    if out is None:
+        out = torch.empty(B, kc, dtype=torch.float64, device=cand_idx.device)
     _lib.call("ttr_tfidf_candidates", cand_idx.contiguous(), B, kc, docs_csr.row_offset, docs_csr.rows,
               docs_csr.indptr, docs_csr.indices, docs_csr.data, q_csr.indptr, q_csr.indices, q_csr.data, out)
     return out
@@ -130,11 +166,14 @@ def tfidf_candidates(cand_idx: torch.Tensor, docs_csr: CsrF64, q_csr: CsrF64) ->
 
 def hybrid_rerank(cand_idx: torch.Tensor, cand_cos: torch.Tensor, alpha: float,
                   docs_csr: Optional[CsrF64] = None, q_csr: Optional[CsrF64] = None,
-                  tfidf: Optional[torch.Tensor] = None, space="l2", top_n: int = 10):
+                  tfidf: Optional[torch.Tensor] = None, space="l2", top_n: int = 10,
+                  q_sqnorm: Optional[torch.Tensor] = None, d_sqnorm: Optional[torch.Tensor] = None):
     """The `/search` rerank (frontend/main.py:158-198) for a batch of queries.
 
     cand_idx int64 [B, kc] (global document ids, dense-rank order), cand_cos fp32 [B, kc].
-    Either (docs_csr, q_csr) or precomputed `tfidf` fp64 [B, kc] must be given.
+    Either (docs_csr, q_csr) or precomputed `tfidf` fp64 [B, kc] must be given.  `q_sqnorm` fp64 [B] /
+    `d_sqnorm` fp64 [B, kc]: squared norms for the general squared-L2 semantic of space 'l2' (zero-vector
+    query of a token-less string, un-normalised model); omitted = unit vectors (2 cos - 1).
     Returns dict(final, semantic, tfidf fp64 [B, top_n], pos int32 [B, top_n], idx int64 [B, top_n])."""
     B, kc = cand_idx.shape
     dev = cand_idx.device
@@ -144,14 +183,18 @@ def hybrid_rerank(cand_idx: torch.Tensor, cand_cos: torch.Tensor, alpha: float,
     sem = torch.empty_like(fin)
     tf = torch.empty_like(fin)
     pos = torch.empty(B, top_n, dtype=torch.int32, device=dev)
+    if q_sqnorm is not None:
+        q_sqnorm = q_sqnorm.to(device=dev, dtype=torch.float64).contiguous()
+    if d_sqnorm is not None:
+        d_sqnorm = d_sqnorm.to(device=dev, dtype=torch.float64).contiguous()
     if tfidf is not None:
         _lib.call("ttr_hybrid_rerank", cand_idx, cand_cos, B, kc, 0, None, None, None, None, None, None,
-                  tfidf.contiguous(), float(alpha), _space_code(space), top_n, fin, sem, tf, pos)
+                  tfidf.contiguous(), q_sqnorm, d_sqnorm, float(alpha), _space_code(space), top_n, fin, sem, tf, pos)
     else:
         if docs_csr is None or q_csr is None:
             raise ValueError("hybrid_rerank needs (docs_csr, q_csr) or tfidf")
         _lib.call("ttr_hybrid_rerank", cand_idx, cand_cos, B, kc, docs_csr.row_offset, docs_csr.indptr,
-                  docs_csr.indices, docs_csr.data, q_csr.indptr, q_csr.indices, q_csr.data, None,
+                  docs_csr.indices, docs_csr.data, q_csr.indptr, q_csr.indices, q_csr.data, None, q_sqnorm, d_sqnorm,
                   float(alpha), _space_code(space), top_n, fin, sem, tf, pos)
     idx = torch.gather(cand_idx, 1, pos.clamp_min(0).long())
     return {"final": fin, "semantic": sem, "tfidf": tf, "pos": pos, "idx": idx}
@@ -166,9 +209,13 @@ def shard_bounds(n_rows: int, world: int, rank: int) -> Tuple[int, int]:
 
 class _PeerExchange:
     """Symmetric-memory candidate buffers: every rank writes its local [B, k] top-k (scores, global
-    ids, optional TF-IDF payload) into its own buffer; after a device-side barrier the merge kernel
-    of every rank reads all R buffers in place over NVLink (ttr_topk_merge_peers) — no all-gather.
-    Two buffers alternate so a fast rank never overwrites what a slow peer is still reading."""
+    ids, optional TF-IDF payload) into its own buffer; ONE kernel per step then signals the peers,
+    waits for their signals (release/acquire flags in the same symmetric allocation) and merges all
+    R lists in place over NVLink (ttr_topk_exchange_merge) — no all-gather, no separate barrier launch.
+    Two list buffers alternate by step parity so a fast rank never overwrites what a slow peer is
+    still reading (a rank can be at most one step ahead: it waits for every peer's flag of its step)."""
+
+    FLAG_BYTES = 256
 
     def __init__(self, group, device, max_b: int, k: int):
         import ctypes
@@ -177,17 +224,25 @@ class _PeerExchange:
         self.ctypes = ctypes
         self.k, self.max_b = k, max_b
         self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
         n = max_b * k
         self.off_s, self.off_i, self.off_t = 0, n * 4, n * 12
         self.stride = (n * 20 + 255) // 256 * 256
-        self.buf = symm.empty(2 * self.stride, dtype=torch.uint8, device=device)
+        self.off_flags = 2 * self.stride
+        self.buf = symm.empty(2 * self.stride + self.FLAG_BYTES, dtype=torch.uint8, device=device)
         grp = group if group is not None else dist.group.WORLD
         self.hdl = symm.rendezvous(self.buf, grp)
         self.ptrs = [int(p) for p in self.hdl.buffer_ptrs]
+        self.buf[self.off_flags:].zero_()
+        torch.cuda.current_stream(device).synchronize()
+        self.hdl.barrier(channel=0)            # every rank's flags are zero before anyone signals step 1
         self.step = 0
+        arr = ctypes.c_uint64 * self.world
+        self._arr = arr
+        self._flags = arr(*[a + self.off_flags for a in self.ptrs])
 
     def views(self, B: int):
-        p = self.step & 1
+        p = (self.step + 1) & 1                # the buffer of the step that `merge` is about to run
         base = p * self.stride
         n = B * self.k
         s = self.buf[base + self.off_s: base + self.off_s + n * 4].view(torch.float32).view(B, self.k)
@@ -196,22 +251,20 @@ class _PeerExchange:
         return s, i, t
 
     def merge(self, B: int, with_tfidf: bool):
-        """Barrier, then one kernel that reads every rank's lists over peer memory."""
+        """One kernel: signal, wait for the peers, read every rank's lists over peer memory, merge."""
         ct = self.ctypes
-        p = self.step & 1
         self.step += 1
-        self.hdl.barrier(channel=p)
-        base = p * self.stride
-        arr = ct.c_uint64 * self.world
-        ps = arr(*[a + base + self.off_s for a in self.ptrs])
-        pi = arr(*[a + base + self.off_i for a in self.ptrs])
-        pt = arr(*[a + base + self.off_t for a in self.ptrs]) if with_tfidf else None
+        base = (self.step & 1) * self.stride
+        ps = self._arr(*[a + base + self.off_s for a in self.ptrs])
+        pi = self._arr(*[a + base + self.off_i for a in self.ptrs])
+        pt = self._arr(*[a + base + self.off_t for a in self.ptrs]) if with_tfidf else None
         dev = self.buf.device
         out_s = torch.empty(B, self.k, dtype=torch.float32, device=dev)
         out_i = torch.empty(B, self.k, dtype=torch.int64, device=dev)
         out_t = torch.empty(B, self.k, dtype=torch.float64, device=dev) if with_tfidf else None
-        _lib.call("ttr_topk_merge_peers", ct.addressof(ps), ct.addressof(pi), ct.addressof(pt) if pt else None,
-                  self.world, B, self.k, self.k, out_s, out_i, out_t)
+        _lib.call("ttr_topk_exchange_merge", ct.addressof(ps), ct.addressof(pi), ct.addressof(pt) if pt else None,
+                  ct.addressof(self._flags), self.world, self.rank, self.step & 0xFFFFFFFF, B, self.k, self.k,
+                  out_s, out_i, out_t)
         return out_s, out_i, out_t
 
 
@@ -238,17 +291,34 @@ class ShardedIndex:
         self._px: Optional[_PeerExchange] = None
 
     def _exchange(self, B: int, k: int) -> Optional[_PeerExchange]:
-        """Symmetric-memory exchange state (created collectively on first use / growth)."""
+        """Symmetric-memory exchange state, created collectively on first use / growth.  The outcome is AGREED
+        across the group (all-reduce MIN of an ok flag): if any rank cannot map its peers (no P2P, out of
+        memory) every rank switches to the NCCL all-gather exchange — a split decision would deadlock.  B and k
+        must be the same on every rank (replicated query batch); that is checked in the same exchange."""
         if not self.peer_memory:
             return None
         if self._px is None or self._px.k != k or self._px.max_b < B:
+            dist = self._dist
+            dev = self.docs.device
+            ok, err = 1, None
             try:
-                self._px = _PeerExchange(self.group, self.docs.device, max(B, 128), k)
-            except Exception as e:     # no P2P mapping on this box: keep the NCCL all-gather exchange
+                px = _PeerExchange(self.group, dev, max(B, 128), k)
+            except Exception as e:     # no P2P mapping on this box
+                ok, err, px = 0, e, None
+            agree = torch.tensor([ok, B, -B, k, -k], dtype=torch.int64, device=dev)
+            dist.all_reduce(agree, op=dist.ReduceOp.MIN, group=self.group)
+            a = agree.tolist()
+            if a[1] != -a[2] or a[3] != -a[4]:
+                raise _lib.TTRError(f"ShardedIndex.search: query batch / k differ across ranks (min B {a[1]}, max B {-a[2]}, "
+                                    f"min k {a[3]}, max k {-a[4]}); every rank must pass the same replicated batch")
+            if a[0] == 0:
                 import warnings
-                warnings.warn(f"peer-memory exchange unavailable ({e!r}); using NCCL all-gather")
+                warnings.warn(f"peer-memory exchange unavailable on at least one rank ({err!r} here); "
+                              "all ranks use the NCCL all-gather exchange")
                 self.peer_memory = False
+                self._px = None
                 return None
+            self._px = px
         return self._px
 
     def _local(self, Q, k, out=None):
@@ -283,7 +353,7 @@ class ShardedIndex:
         return topk_merge(gs, gi, k)
 
     def search_hybrid(self, Q: torch.Tensor, q_csr: CsrF64, alpha: float, k: int = 50, top_n: int = 10,
-                      space="l2"):
+                      space="l2", q_sqnorm: Optional[torch.Tensor] = None):
         """Dense top-k -> TF-IDF of the candidates (each rank scores the rows it owns) ->
         blend -> top_n.  Candidate TF-IDF scores travel with the candidates in the same
         all-gather, so no rank needs another rank's CSR slice."""
@@ -296,9 +366,9 @@ class ShardedIndex:
             B = Q.shape[0]
             vs, vi, vt = px.views(B)
             self._local(Q, k, out=(vs, vi))
-            vt.copy_(tfidf_candidates(vi, self.tfidf, q_csr))
+            tfidf_candidates(vi, self.tfidf, q_csr, out=vt)
             s, i, tf = px.merge(B, with_tfidf=True)
-            out = hybrid_rerank(i, s, alpha, tfidf=tf, space=space, top_n=top_n)
+            out = hybrid_rerank(i, s, alpha, tfidf=tf, space=space, top_n=top_n, q_sqnorm=q_sqnorm)
             out["dense_scores"], out["dense_idx"] = s, i
             return out
         s, i = self._local(Q, k)
@@ -323,6 +393,6 @@ class ShardedIndex:
             i = torch.where(valid, torch.gather(flat_i, 1, msrc_c), torch.full_like(msrc, -1))
             tf = torch.where(valid, torch.gather(flat_t, 1, msrc_c), torch.zeros_like(ms, dtype=torch.float64))
             s = ms
-        out = hybrid_rerank(i, s, alpha, tfidf=tf, space=space, top_n=top_n)
+        out = hybrid_rerank(i, s, alpha, tfidf=tf, space=space, top_n=top_n, q_sqnorm=q_sqnorm)
         out["dense_scores"], out["dense_idx"] = s, i
         return out

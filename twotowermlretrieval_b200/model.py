@@ -151,14 +151,14 @@ class RNNEncoder(nn.Module):
     def _views_ok(self) -> bool:
         base = self._flat.data_ptr()
         for name, p in _flat_order(self):
-            o, _ = self._slices.get(self._prefix + name, (None, None))
+            o, _ = self._slices.get(name, (None, None))
             if o is None or p.data_ptr() != base + 4 * o:
                 return False
         return True
 
     def _w(self, name: str, shape) -> torch.Tensor:
         owner = self._owner if self._owner is not None else self
-        o, _ = owner._slices[self._prefix + name]
+        o, _ = owner._slices[(self._prefix + name) if self._owner is not None else name]
         n = int(np.prod(shape))
         return owner._flat[o:o + n].view(*shape)
 
@@ -251,7 +251,17 @@ class _OwnerRef:
         self._o = owner
 
     def __getattr__(self, k):
+        # copy / pickle probe dunders (`__deepcopy__`, `__setstate__`, ...) on a not-yet-initialised instance
+        if k.startswith("__") or "_o" not in self.__dict__:
+            raise AttributeError(k)
         return getattr(self.__dict__["_o"], k)
+
+    def __deepcopy__(self, memo):
+        # `copy.deepcopy(model)` (the usual way to snapshot a best model; the reference nn.Module supports it):
+        # the handle of the copy must point at the COPY of the owner, which deepcopy has already registered in
+        # `memo`; an encoder copied on its own becomes a stand-alone module
+        new_owner = memo.get(id(self.__dict__["_o"]))
+        return _OwnerRef(new_owner) if new_owner is not None else None
 
 
 def triplet_loss_cosine(triplet: Tuple[torch.Tensor, torch.Tensor, torch.Tensor], margin: float = 0.2) -> torch.Tensor:

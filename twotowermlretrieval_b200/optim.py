@@ -75,12 +75,16 @@ class FusedClipAdam:
         _lib.call("ttr_clip_adam", flat, grads, self._m, self._v, flat.numel(), float(scale),
                   float(max_norm if max_norm is not None else -1.0), float(g["lr"]), float(g["betas"][0]),
                   float(g["betas"][1]), float(g["eps"]), int(self.step_count), self.last_grad_norm, self._ws)
+        # the kernel updated the parameters through raw pointers: invalidate caches keyed on the parameter state
+        self.model._param_epoch = getattr(self.model, "_param_epoch", 0) + 1
         if self._extra is not None:
             self._extra.step()
 
     def state_dict(self):
         return {"step": self.step_count, "exp_avg": self._m, "exp_avg_sq": self._v,
-                "param_groups": self.param_groups}
+                "param_groups": self.param_groups,
+                # moments of a trainable embedding table (delegated to torch.optim.Adam)
+                "embedding_adam": self._extra.state_dict() if self._extra is not None else None}
 
     def load_state_dict(self, sd):
         self.step_count = int(sd["step"])
@@ -88,3 +92,5 @@ class FusedClipAdam:
         if sd.get("exp_avg") is not None:
             self._m.copy_(sd["exp_avg"])
             self._v.copy_(sd["exp_avg_sq"])
+        if self._extra is not None and sd.get("embedding_adam") is not None:
+            self._extra.load_state_dict(sd["embedding_adam"])

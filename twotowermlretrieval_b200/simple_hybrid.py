@@ -15,8 +15,7 @@ from typing import List, Tuple
 import numpy as np
 import torch
 
-from . import _lib
-from .index import CsrF64, _SEARCH_LOCK
+from .index import KMAX, CsrF64, blend_topk
 from .query_inferencer import QueryInferencer
 
 
@@ -30,7 +29,6 @@ class SimpleHybridRetriever:
         self.doc_embeddings = None          # np.float32 [N, H], like the reference attribute
         self._doc_dev = None                # resident copy, fp32 [N, H]
         self._csr = None                    # resident TF-IDF matrix
-        self._ws = None
 
     def fit(self, documents: List[str]):
         self.documents = list(documents)
@@ -44,21 +42,16 @@ class SimpleHybridRetriever:
         dev = self._doc_dev.device
         N, D = self._doc_dev.shape
         k = min(top_k, N)
+        if not 1 <= k <= KMAX:
+            raise ValueError(f"SimpleHybridRetriever.search: top_k={top_k} outside [1, {KMAX}] — the fused blend + "
+                             "top-k kernel keeps at most 64 results per query (the reference default is 10)")
         q_row = self.tfidf.transform([query]).tocsr()
         q_row.sort_indices()
         q_idx = torch.as_tensor(q_row.indices.astype(np.int32), device=dev)
         q_val = torch.as_tensor(q_row.data.astype(np.float64), device=dev)
         q_np = self.dense_retriever.get_query_embedding(query)
         q = torch.from_numpy(q_np).to(dev)
-        lib = _lib.load()
-        nbytes = lib.ttr_blend_topk_workspace_bytes(k)
-        if self._ws is None or self._ws.numel() < nbytes:
-            self._ws = torch.empty(int(nbytes), dtype=torch.uint8, device=dev)
-        out_s = torch.empty(k, dtype=torch.float64, device=dev)
-        out_i = torch.empty(k, dtype=torch.int64, device=dev)
-        with _SEARCH_LOCK:                  # the per-object workspace is shared by concurrent callers
-            _lib.call("ttr_blend_topk", q, float(np.linalg.norm(q_np)), self._doc_dev, N, D, self._csr.indptr,
-                  self._csr.indices, self._csr.data, q_idx, q_val, int(q_idx.numel()), float(self.alpha), k,
-                  out_s, out_i, None, self._ws)
+        out_s, out_i = blend_topk(q, float(np.linalg.norm(q_np)), self._doc_dev, self._csr, q_idx, q_val,
+                                  self.alpha, k)
         idx, sc = out_i.cpu().tolist(), out_s.cpu().tolist()
         return [(self.documents[i], s) for i, s in zip(idx, sc) if i >= 0]

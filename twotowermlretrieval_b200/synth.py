@@ -12,7 +12,7 @@ from __future__ import annotations
 import numpy as np
 
 __all__ = [
-    "tower_param_shapes", "make_state_dict", "make_tokens", "make_lengths",
+    "tower_param_shapes", "make_state_dict", "make_tokens", "make_ragged_tokens", "make_lengths",
     "pad_rows", "make_unit_rows", "make_tfidf_csr", "default_config",
 ]
 
@@ -106,6 +106,21 @@ def make_tokens(n: int, kind: str, vocab_size: int, seed: int = 2,
     flat = (np.searchsorted(cdf, rng.random(total), side="left") + 1).astype(np.int64)
     np.clip(flat, 1, vocab_size - 1, out=flat)
     return pad_rows(flat, lengths, pad_to), lengths
+
+
+def make_ragged_tokens(n: int, kind: str, vocab_size: int, seed: int = 2, chunk: int = 1 << 22):
+    """(flat int64 ids, lengths int64 [n]) — the same distributions as `make_tokens` without the padded matrix
+    (bulk-encode inputs: 1.1 M passages are 72 M tokens, their padded [n, 256] form would be 2.3 GB)."""
+    rng = np.random.default_rng(seed)
+    lengths = make_lengths(n, kind, rng)
+    cdf = _zipf_cdf(vocab_size, 1.07)
+    total = int(lengths.sum())
+    flat = np.empty(total, dtype=np.int64)
+    for lo in range(0, total, chunk):
+        hi = min(total, lo + chunk)
+        flat[lo:hi] = np.searchsorted(cdf, rng.random(hi - lo), side="left") + 1
+    np.clip(flat, 1, vocab_size - 1, out=flat)
+    return flat, lengths
 
 
 def pad_rows(flat: np.ndarray, lengths: np.ndarray, pad_to: "int | None" = None) -> np.ndarray:

@@ -49,7 +49,7 @@ def input_projection(A: torch.Tensor, W: torch.Tensor, bias: torch.Tensor, out: 
 class SeqPlan:
     """Device-resident packing plan of one padded id batch."""
 
-    def __init__(self, ids: torch.Tensor):
+    def __init__(self, ids: torch.Tensor, token_bound: Optional[int] = None):
         B, T = ids.shape
         dev = ids.device
         self.B, self.T = B, T
@@ -59,13 +59,34 @@ class SeqPlan:
         self.offsets = torch.empty(B + 1, dtype=torch.int32, device=dev)
         self.status = torch.empty(4, dtype=torch.int32, device=dev)
         _lib.call("ttr_seq_plan", ids, B, T, self.lengths, self.order, self.offsets, self.status)
-        self.m_bound = B * T
+        # rows allocated for the packed per-token matrices: B*T unless the caller knows the token count
+        # (bulk encode: the host tokenised the rows) — rounded up to a 128-row GEMM tile
+        self.m_bound = B * T if token_bound is None else min(B * T, (int(token_bound) + 127) // 128 * 128)
         self.total = self.offsets[B:]          # device scalar view: number of packed tokens
 
     def check_lengths(self):
         st = self.status.cpu()
         if int(st[0]) > 0:
             raise RuntimeError(_ZERO_LEN_MSG)
+
+
+def _w16_cached(enc, layer: int, W_ih: torch.Tensor) -> torch.Tensor:
+    """fp16 copy of a layer's W_ih for the kind::f16 projection, converted once per parameter state: the key is
+    the weights' address, torch's version counters of the parameters and of the flat buffer they are views of
+    (bumped by in-place torch updates, optimiser steps, load_state_dict) and the owner's `_param_epoch`
+    (bumped by FusedClipAdam, whose kernel writes through raw pointers)."""
+    owner = enc._owner if enc._owner is not None else enc
+    pv = tuple(getattr(enc.rnn, f"weight_ih_l{layer}{sfx}")._version
+               for sfx in ([""] + (["_reverse"] if enc.bidirectional else [])))
+    key = (W_ih.data_ptr(), W_ih._version, pv, getattr(owner, "_param_epoch", 0))
+    cache = enc.__dict__.setdefault("_w16_cache", {})
+    hit = cache.get(layer)
+    if hit is not None and hit[0] == key:
+        return hit[1]
+    W16 = torch.empty(W_ih.shape, dtype=torch.float16, device=W_ih.device)
+    _lib.call("ttr_f32_to_f16", W_ih.detach().contiguous(), W16, W_ih.numel())
+    cache[layer] = (key, W16)
+    return W16
 
 
 def _forward_layers_f16(enc, ids, plan, B, T, H, E, dirs, table, dev) -> torch.Tensor:
@@ -79,8 +100,7 @@ def _forward_layers_f16(enc, ids, plan, B, T, H, E, dirs, table, dev) -> torch.T
     layer_in, h_last = X, None
     for layer in range(enc.num_layers):
         W_ih, b_ih, W_hh, b_hh = enc.layer_weights(layer)
-        W16 = torch.empty(W_ih.shape, dtype=torch.float16, device=dev)
-        _lib.call("ttr_f32_to_f16", W_ih.detach().contiguous(), W16, W_ih.numel())
+        W16 = _w16_cached(enc, layer, W_ih)
         gi = torch.empty(Mb, dirs * 3 * H, dtype=torch.float16, device=dev)
         _lib.call("ttr_gemm_f16_bias", layer_in, W16, b_ih.detach(), gi, Mb, plan.total, dirs * 3 * H, layer_in.shape[1])
         last = layer == enc.num_layers - 1
@@ -113,7 +133,7 @@ def _forward_impl(enc, ids: torch.Tensor, need_grad: bool, training: bool):
     if table.device != dev:
         raise _lib.TTRError("embedding table and ids are on different devices")
 
-    plan = SeqPlan(ids)
+    plan = SeqPlan(ids, getattr(enc, "_token_bound", None) if not need_grad else None)
     if enc.strict_lengths:
         plan.check_lengths()
     Mb = plan.m_bound
