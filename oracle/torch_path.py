@@ -39,7 +39,9 @@ def _gru_layer(packed, sd, prefix, layer: int, bi: bool):
                  sd[f"{prefix}.rnn.bias_ih_l{layer}{sfx}"], sd[f"{prefix}.rnn.bias_hh_l{layer}{sfx}"]]
     nb = int(packed.batch_sizes[0])
     hx = torch.zeros((2 if bi else 1), nb, H, dtype=packed.data.dtype, device=packed.data.device)
-    out, hn = torch._VF.gru(packed.data, packed.batch_sizes, hx, flat, True, 1, 0.0, False, bi)
+    # `train` only selects dropout (0.0 here) on CPU; cuDNN additionally refuses a backward pass after train=False
+    train = torch.is_grad_enabled() and any(t.requires_grad for t in flat)
+    out, hn = torch._VF.gru(packed.data, packed.batch_sizes, hx, flat, True, 1, 0.0, train, bi)
     return out, hn
 
 

@@ -245,9 +245,11 @@ def test_headline_corpus_8p8M_docs(cuda_device, B, n_check):
     assert torch.equal(i, i2) and torch.equal(s, s2)
 
 
-@pytest.mark.parametrize("B,N", [(128, 300_000), (256, 300_000), (300, 150_000), (1024, 100_000), (40, 70_001)])
+@pytest.mark.parametrize("B,N", [(128, 300_000), (256, 300_000), (300, 150_000), (1024, 100_000), (40, 70_001), (129, 33),
+                                 (512, 1_000_003)])
 def test_id_segments_and_fast_reject(cuda_device, B, N):
-    """A CTA numbers its candidates with 16 bits inside a segment and publishes its list at every segment boundary;
+    """B > 128 runs CTA PAIRS (tcgen05.mma.cta_group::2, 64-document tiles, each CTA loads half of every tile).
+    A CTA numbers its candidates with 16 bits inside a segment and publishes its list at every segment boundary;
     debug bit 24 shrinks the segments to 16 tiles so a small corpus crosses dozens of boundaries (the production
     length is 2,048 tiles: B >= 256 on the full corpus).  Exact, so: identical to the default segmentation, to the
     two-pass path, and to the epilogue without the max-tree fast reject (bit 25)."""
@@ -256,7 +258,8 @@ def test_id_segments_and_fast_reject(cuda_device, B, N):
     D[N // 2:N // 2 + 300] = D[100:400]                       # exact ties across slices and segments
     Q = torch.tensor(synth.make_unit_rows(B, 256, seed=80 + B), device=cuda_device)
     s_a, i_a = search_topk(Q, D, 50)
-    for flags in (1 << 24, (1 << 24) | (1 << 21), 1 << 25, (1 << 24) | (1 << 25), 1 << 21):
+    # bit 27: one CTA per query tile (round-1 layout) instead of CTA pairs for B > 128
+    for flags in (1 << 24, (1 << 24) | (1 << 21), 1 << 25, (1 << 24) | (1 << 25), 1 << 21, 1 << 27, (1 << 27) | (1 << 24)):
         _lib.call_nostream("ttr_debug_set_flags", flags)
         try:
             s_b, i_b = search_topk(Q, D, 50)

@@ -296,14 +296,30 @@ struct FusedArgs {
   int sample_tiles;         // tiles per CTA in the sample phase
 };
 
-template <int MODE>
-__global__ void __launch_bounds__(SM_THREADS, 1)
-score_topk_mma_kernel(const float* __restrict__ Q, const __grid_constant__ CUtensorMap map_d, int B, int64_t N,
-                      int k, int n_slices, float* __restrict__ tau_g, float* __restrict__ out_s,
-                      int32_t* __restrict__ out_i, int32_t* __restrict__ out_n, long long* __restrict__ trace,
-                      int dbg, FusedArgs fa, int seg_tiles, int cap) {
+// PAIR = true (query batches > 128): the two CTAs of a cluster own two adjacent 128-query tiles and the SAME document
+// slice, and run ONE tcgen05.mma.cta_group::2 (M = 256) per k-step over 64-document tiles: each CTA stages its own
+// queries in its own tensor memory and loads only ITS HALF (32 documents) of every tile; the tensor cores of both SMs
+// read both halves.  Per SM that halves the document bytes delivered per unit of MMA work: with one CTA per query tile
+// the L2 -> SM fabric saturated at ~7-8 TB/s (two CTAs fetching every tile: B = 256 ran at 0.55 of HBM, r2 traces);
+// a pair fetches every tile once, so B = 256 is HBM-bound like B = 128.  Rank 0 (the leader) issues the MMAs; the
+// TMA loads of both CTAs count their bytes on the leader's `full` barrier; tcgen05.commit multicasts `stage free` and
+// `accumulator full` to both CTAs; the peer's epilogue warps release accumulators with remote arrives on the
+// leader's `accumulator empty` barrier.
+template <int MODE, bool PAIR>
+__device__ __forceinline__ void
+scorer_body(const float* __restrict__ Q, const CUtensorMap& map_d, int B, int64_t N,
+            int k, int n_slices, float* __restrict__ tau_g, float* __restrict__ out_s,
+            int32_t* __restrict__ out_i, int32_t* __restrict__ out_n, long long* __restrict__ trace,
+            int dbg, FusedArgs fa, int seg_tiles, int cap) {
   constexpr bool SAMPLE = MODE == 1;
   constexpr bool FUSED = MODE == 2;
+  constexpr int ND_T = PAIR ? 2 * SM_ND : SM_ND;       // documents per (pair-)tile == accumulator columns per buffer
+  constexpr int HALVES = PAIR ? 2 : 1;                 // 32-column accumulator halves the epilogue reads per tile
+  const uint32_t cta_rank = PAIR ? ptx::cluster_ctarank() : 0u;
+  const bool leader = cta_rank == 0u;
+  // which 32 documents of a 64-document pair tile this CTA loads: B rows [0, 32) come from rank 0's shared memory,
+  // rows [32, 64) from rank 1's (debug bit 26 swaps the assignment: bring-up switch for that convention)
+  const int my_half = PAIR ? (int)(cta_rank ^ ((dbg >> 26) & 1u)) : 0;
   extern __shared__ unsigned char smem_raw[];
   unsigned char* base = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
   unsigned char* ring = base;                                      // [stages][SM_KB][32 rows][128 B]
@@ -331,7 +347,7 @@ score_topk_mma_kernel(const float* __restrict__ Q, const __grid_constant__ CUten
   const int qt = blockIdx.x;                 // query tile
   const int slice = blockIdx.y;              // document slice
   const int q0 = qt * SM_MQ;
-  const int64_t n_tiles = ceil_div64(N, (int64_t)SM_ND);
+  const int64_t n_tiles = ceil_div64(N, (int64_t)ND_T);
   // this CTA's tile sequence: [FUSED: its first S tiles once more in front,] then tiles slice, slice + n_slices, ...
   const int n_mine = slice < n_tiles ? (int)((n_tiles - slice + n_slices - 1) / n_slices) : 0;
   const int S = FUSED ? fa.sample_tiles : 0;
@@ -340,13 +356,14 @@ score_topk_mma_kernel(const float* __restrict__ Q, const __grid_constant__ CUten
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < SM_STAGES; ++s) { ptx::mbar_init(full_bar + s, 1); ptx::mbar_init(empty_bar + s, 1); }
-    for (int b = 0; b < SM_NACC; ++b) { ptx::mbar_init(acc_full + b, 1); ptx::mbar_init(acc_empty + b, 4); }
+    // accumulator release: the four epilogue warps of this CTA (+ the four of the peer, on the leader's barrier)
+    for (int b = 0; b < SM_NACC; ++b) { ptx::mbar_init(acc_full + b, 1); ptx::mbar_init(acc_empty + b, PAIR ? 8 : 4); }
     ptx::mbar_init(&probe_bar, 1);
     ptx::fence_mbar_init();
   }
   if (warp == 2) {
-    ptx::tmem_alloc(tmem_slot, SM_TMEM_COLS);
-    ptx::tmem_relinquish();
+    if (PAIR) { ptx::tmem_alloc_2cta(tmem_slot, SM_TMEM_COLS); ptx::tmem_relinquish_2cta(); }
+    else { ptx::tmem_alloc(tmem_slot, SM_TMEM_COLS); ptx::tmem_relinquish(); }
   }
   ptx::tc_fence_before_sync();
   __syncthreads();
@@ -383,7 +400,8 @@ score_topk_mma_kernel(const float* __restrict__ Q, const __grid_constant__ CUten
     ptx::tmem_st_wait();
   }
   ptx::tc_fence_before_sync();
-  __syncthreads();
+  // pair: the leader's MMAs read the PEER's staged queries and signal its barriers too -> cluster-wide barrier
+  if (PAIR) ptx::cluster_sync(); else __syncthreads();
   ptx::tc_fence_after_sync();
 
   if (threadIdx.x == 0) SM_MARK(1);          // prologue done (TMEM allocated, queries staged)
@@ -396,19 +414,29 @@ score_topk_mma_kernel(const float* __restrict__ Q, const __grid_constant__ CUten
       const uint32_t ph = (uint32_t)(it / SM_STAGES) & 1u;
       ptx::mbar_wait(empty_bar + s, ph ^ 1u);
       unsigned char* dst = ring + s * SM_STAGE_BYTES;
-      const int32_t d0 = (int32_t)(t * SM_ND);
+      const int32_t d0 = (int32_t)(t * ND_T) + my_half * SM_ND;
       if (ptx::elect_one()) {
-        ptx::mbar_arrive_expect_tx(full_bar + s, SM_STAGE_BYTES);
+        if (PAIR) {
+          // both CTAs' bytes are counted on the LEADER's barrier (one arrival: the leader's expect_tx for 2 x 32 KB; a
+          // peer load that lands first only drives the transaction count negative until then)
+          if (leader) ptx::mbar_arrive_expect_tx(full_bar + s, 2 * SM_STAGE_BYTES);
+          const uint32_t bar0 = ptx::mapa(ptx::smem_u32(full_bar + s), 0u);
 #pragma unroll
-        for (int kb = 0; kb < SM_KB; ++kb)
-          ptx::tma_load_2d(dst + kb * SM_D_KB_BYTES, &map_d, kb * 32, d0, full_bar + s);
+          for (int kb = 0; kb < SM_KB; ++kb)
+            ptx::tma_load_2d_2cta(dst + kb * SM_D_KB_BYTES, &map_d, kb * 32, d0, bar0);
+        } else {
+          ptx::mbar_arrive_expect_tx(full_bar + s, SM_STAGE_BYTES);
+#pragma unroll
+          for (int kb = 0; kb < SM_KB; ++kb)
+            ptx::tma_load_2d(dst + kb * SM_D_KB_BYTES, &map_d, kb * 32, d0, full_bar + s);
+        }
       }
       __syncwarp();
       SM_TRACE(0, it);
     }
-  } else if (warp == 1) {
-    // ===== MMA issuer (whole warp runs the loop; one elected lane issues) =====
-    constexpr uint32_t idesc = ptx::make_idesc_tf32(SM_MQ, SM_ND);
+  } else if (warp == 1 && leader) {
+    // ===== MMA issuer (whole warp runs the loop; one elected lane issues; pair: the leader CTA only) =====
+    constexpr uint32_t idesc = ptx::make_idesc_tf32(PAIR ? 2 * SM_MQ : SM_MQ, ND_T);
     for (int it = 0; it < n_seq; ++it) {
       const int64_t t = tile_at(it);
       const int s = it % SM_STAGES;
@@ -420,7 +448,7 @@ score_topk_mma_kernel(const float* __restrict__ Q, const __grid_constant__ CUten
       ptx::tc_fence_after_sync();
       SM_TRACE(1, it);
       const uint32_t d_addr = ptx::smem_u32(ring + ((dbg & 16) ? 0 : s) * SM_STAGE_BYTES);
-      const uint32_t d_tmem = tmem_acc + buf * SM_ACC_COLS;
+      const uint32_t d_tmem = tmem_acc + buf * ND_T;
       const uint64_t b_desc0 = ptx::make_kmajor_sw128_desc(d_addr);
       if (ptx::elect_one()) {
         // Measured (profiles/r1_score_topk_mma_v3_trace_b16.txt vs v4): one accumulation chain
@@ -434,11 +462,17 @@ score_topk_mma_kernel(const float* __restrict__ Q, const __grid_constant__ CUten
             const int ks = c * (32 / SM_KSPLIT) + kk;              // k-step 0..31 (8 floats each)
             // k-block (ks>>2) starts (ks>>2)*4 KB further (>>4 in descriptor units); 32 B per k-step inside it
             const uint64_t b_desc = b_desc0 + (uint64_t)(((dbg & 32) ? 0 : (ks >> 2)) * (SM_D_KB_BYTES >> 4) + 2 * (ks & 3));
-            ptx::mma_tf32_ts(d_tmem + c * SM_ND, tmem_base + ks * 8, b_desc, idesc, kk != 0);
+            if (PAIR) ptx::mma_tf32_ts_2cta(d_tmem, tmem_base + ks * 8, b_desc, idesc, kk != 0);
+            else ptx::mma_tf32_ts(d_tmem + c * SM_ND, tmem_base + ks * 8, b_desc, idesc, kk != 0);
           }
         }
-        ptx::mma_commit(empty_bar + s);
-        ptx::mma_commit(acc_full + buf);
+        if (PAIR) {
+          ptx::mma_commit_2cta(empty_bar + s, 3);       // both CTAs' producers may refill this stage
+          ptx::mma_commit_2cta(acc_full + buf, 3);      // both CTAs' epilogues may read this accumulator
+        } else {
+          ptx::mma_commit(empty_bar + s);
+          ptx::mma_commit(acc_full + buf);
+        }
         if (dbg & 64) ptx::mma_commit(&probe_bar);
       }
       __syncwarp();
@@ -471,48 +505,13 @@ score_topk_mma_kernel(const float* __restrict__ Q, const __grid_constant__ CUten
     float tg_pending = tg;
     // one tile of the epilogue; `smp` (compile-time) selects the register top-4 path of the sample phase.  Two
     // instantiations instead of a runtime flag: with the flag in the loop the main pass ran 10 % slower.
-    auto tile_body = [&](const int it, auto smp_tag) {
+    // Filter one 32-score accumulator half: documents d0 .. d0 + 31, list ids lid0 + j.
+    auto filter32 = [&](const float (&sc32)[32], const int64_t d0, const int lid0, auto smp_tag) {
       constexpr bool smp = decltype(smp_tag)::value;
-      const int64_t t = tile_at(it);
-      const int buf = it % SM_NACC;
-      const uint32_t aph = (uint32_t)(it / SM_NACC) & 1u;
-      if ((it & 7) == 0 && q_valid && !smp) {
-        tg = fmaxf(tg, tg_pending);
-        tg_pending = __ldcg(tau_g + q);
-      }
-      ptx::mbar_wait(acc_full + buf, aph);
-      ptx::tc_fence_after_sync();
-      if (qw == 0) SM_TRACE(3, it);
-      float sc32[32];
-      {
-        uint32_t r[32];
-        const uint32_t tcol = tmem_acc + ((uint32_t)(qw * 32) << 16) + buf * SM_ACC_COLS;
-        if (!(dbg & 8)) {
-          ptx::tmem_ld_32x32(tcol, r);
-          ptx::tmem_ld_wait();
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) r[j] = 0;
-        }
-#pragma unroll
-        for (int j = 0; j < 32; ++j) sc32[j] = __uint_as_float(r[j]);
-#pragma unroll
-        for (int c = 1; c < ((dbg & 8) ? 1 : SM_KSPLIT); ++c) {
-          ptx::tmem_ld_32x32(tcol + c * SM_ND, r);
-          ptx::tmem_ld_wait();
-#pragma unroll
-          for (int j = 0; j < 32; ++j) sc32[j] += __uint_as_float(r[j]);
-        }
-      }
-      ptx::tc_fence_before_sync();
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(acc_empty + buf);
-      if (qw == 0) SM_TRACE(4, it);
-      const int64_t d0 = t * SM_ND;
       // one threshold, one compare per score: "strictly above tau" == ">= next float above tau"
       const float thr = smp ? key2f(f2key(top_s[SM_SAMPLE_TOP - 1]) + 1u)         // must beat the weakest kept score
                             : fmaxf(tg, strict ? key2f(f2key(tau) + 1u) : tau);
-      // Fast reject: the maximum of the thread's 32 scores (a 5-level FMNMX tree, ~35 issue slots) against the
+      // Fast reject: the maximum of the thread's 32 scores (a 5-level FMNMX tree, ~25 issue slots) against the
       // threshold, one vote per warp.  After the sample pass seeded the bounds only ~1 tile in 4 holds a survivor
       // for ANY of a warp's 32 queries (r2 traces: the per-score mask build + OR-reduce + compaction vote below
       // cost ~610 of the epilogue's ~1100 cycles per tile whether or not anything survived).
@@ -528,14 +527,14 @@ score_topk_mma_kernel(const float* __restrict__ Q, const __grid_constant__ CUten
           for (int j = 0; j < w; ++j) m16[j] = fmaxf(m16[j], m16[j + w]);
         skip = !tail && !__any_sync(0xffffffffu, m16[0] >= thr);
       }
-      if (!skip) {
+      if (skip) return;
       // Branch-free filter -> per-lane bit mask of surviving documents.  (A short-circuit
       // condition compiles to a branch per score: ~45 cycles of resolve latency each with one
       // warp per scheduler, 1300-1600 cycles per tile; profiles/r1_score_topk_mma_v4_trace_*.)
       uint32_t mask = 0;
 #pragma unroll
       for (int j = 0; j < 32; ++j) mask |= (sc32[j] >= thr ? 1u : 0u) << j;
-      if (tail) mask &= (N - d0 >= 32) ? 0xffffffffu : ((1u << (int)(N - d0)) - 1u);
+      if (tail) mask &= (N - d0 >= 32) ? 0xffffffffu : (N <= d0 ? 0u : ((1u << (int)(N - d0)) - 1u));
       // Visit only the documents that survive in SOME lane (warp-uniform loop over the OR of
       // the lane masks, usually 0-2 bits): traversing 32 conditional regions costs ~1500 cycles
       // per tile even when nothing is appended (profiles/r1_score_topk_mma_v4_trace_*).
@@ -566,19 +565,61 @@ score_topk_mma_kernel(const float* __restrict__ Q, const __grid_constant__ CUten
             cs = up ? ts : cs;
             ci = up ? ti : ci;
           }
-        } else if ((mask >> j) & 1u) {   // cnt <= SM_CAP - SM_ND before the tile, so 32 free slots exist
+        } else if ((mask >> j) & 1u) {   // cnt <= SM_CAP - SM_ND before every half, so 32 free slots exist
           ls[cnt * SM_MQ] = scj;
-          li[cnt * SM_MQ] = (uint16_t)((it - S - seg_base) * SM_ND + j);
+          li[cnt * SM_MQ] = (uint16_t)(lid0 + j);
           ++cnt;
         }
       }
-      if (qw == 0) SM_TRACE(6, it);
       if (!smp && __any_sync(0xffffffffu, cnt > SM_CAP - SM_ND)) {
         __syncwarp();
         cnt = thread_compact(ls, li, cnt, k, tau, strict);
         if (q_valid && cnt >= k) atomic_max_float(tau_g + q, tau);
       }
+    };
+    // one (pair-)tile of the epilogue; `smp` (compile-time) selects the register top-4 path of the sample phase.  Two
+    // instantiations instead of a runtime flag: with the flag in the loop the main pass ran 10 % slower.
+    auto tile_body = [&](const int it, auto smp_tag) {
+      constexpr bool smp = decltype(smp_tag)::value;
+      const int64_t t = tile_at(it);
+      const int buf = it % SM_NACC;
+      const uint32_t aph = (uint32_t)(it / SM_NACC) & 1u;
+      if ((it & 7) == 0 && q_valid && !smp) {
+        tg = fmaxf(tg, tg_pending);
+        tg_pending = __ldcg(tau_g + q);
       }
+      ptx::mbar_wait(acc_full + buf, aph);
+      ptx::tc_fence_after_sync();
+      if (qw == 0) SM_TRACE(3, it);
+      float sc[HALVES][32];
+      {
+        const uint32_t tcol = tmem_acc + ((uint32_t)(qw * 32) << 16) + buf * ND_T;
+#pragma unroll
+        for (int h = 0; h < HALVES; ++h) {
+          uint32_t r[32];
+          if (!(dbg & 8)) {
+            ptx::tmem_ld_32x32(tcol + h * SM_ND, r);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) r[j] = 0;
+          }
+#pragma unroll
+          for (int j = 0; j < 32; ++j) sc[h][j] = __uint_as_float(r[j]);
+        }
+        if (!(dbg & 8)) ptx::tmem_ld_wait();
+      }
+      ptx::tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) {
+        // the accumulator may be overwritten: tell the MMA issuer (pair: it lives in the leader CTA)
+        if (!PAIR || leader) ptx::mbar_arrive(acc_empty + buf);
+        else ptx::mbar_arrive_cluster(ptx::mapa(ptx::smem_u32(acc_empty + buf), 0u));
+      }
+      if (qw == 0) SM_TRACE(4, it);
+#pragma unroll
+      for (int h = 0; h < HALVES; ++h)
+        filter32(sc[h], t * ND_T + h * SM_ND, (it - S - seg_base) * ND_T + h * SM_ND, smp_tag);
+      if (qw == 0) SM_TRACE(6, it);
       if (qw == 0) SM_TRACE(7, it);
     };
     // Publish the list: at most SM_KEEP candidates at or above the global bound go to the per-query
@@ -599,7 +640,7 @@ score_topk_mma_kernel(const float* __restrict__ Q, const __grid_constant__ CUten
           if (e < cnt && ls[e * SM_MQ] >= tgf) {
             const int lid = li[e * SM_MQ];                     // local -> global: tile = slice + main_tile * n_slices
             out_s[ob] = ls[e * SM_MQ];
-            out_i[ob] = (int32_t)(((int64_t)slice + (int64_t)(seg_base + (lid >> 5)) * n_slices) * SM_ND + (lid & 31));
+            out_i[ob] = (int32_t)(((int64_t)slice + (int64_t)(seg_base + lid / ND_T) * n_slices) * ND_T + lid % ND_T);
             ++ob;
           }
       }
@@ -670,8 +711,12 @@ score_topk_mma_kernel(const float* __restrict__ Q, const __grid_constant__ CUten
 
   if (threadIdx.x == 128) SM_MARK(3);        // candidates published
   ptx::tc_fence_before_sync();
-  __syncthreads();
-  if (warp == 2) ptx::tmem_dealloc(tmem_base, SM_TMEM_COLS);
+  // pair: no CTA may leave (or free tensor memory) while the peer's MMAs / commits / remote arrives still target it
+  if (PAIR) ptx::cluster_sync(); else __syncthreads();
+  if (warp == 2) {
+    if (PAIR) ptx::tmem_dealloc_2cta(tmem_base, SM_TMEM_COLS);
+    else ptx::tmem_dealloc(tmem_base, SM_TMEM_COLS);
+  }
   if (threadIdx.x == 0) SM_MARK(4);          // kernel exit
   if (trace && (dbg & (1 << 20)) && threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y < SM_TRACE_TILES) {
     long long gt;
@@ -679,6 +724,15 @@ score_topk_mma_kernel(const float* __restrict__ Q, const __grid_constant__ CUten
     trace[6 * SM_TRACE_TILES + blockIdx.y] = gt;
   }
 #undef SM_MARK
+}
+
+template <int MODE, bool PAIR>
+__global__ void __launch_bounds__(SM_THREADS, 1)
+score_topk_mma_kernel(const float* __restrict__ Q, const __grid_constant__ CUtensorMap map_d, int B, int64_t N,
+                      int k, int n_slices, float* __restrict__ tau_g, float* __restrict__ out_s,
+                      int32_t* __restrict__ out_i, int32_t* __restrict__ out_n, long long* __restrict__ trace,
+                      int dbg, FusedArgs fa, int seg_tiles, int cap) {
+  scorer_body<MODE, PAIR>(Q, map_d, B, N, k, n_slices, tau_g, out_s, out_i, out_n, trace, dbg, fa, seg_tiles, cap);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -872,20 +926,25 @@ static int launch_select_merge(const float* outs, const int32_t* outi, const int
 
 struct MmaPlan {
   int n_qt, n_slices, n_ctas;
+  bool pair;                        // CTA pairs (cta_group::2, 64-document tiles): every batch of more than one query tile
+  int nd_t;                         // documents per tile: 32, pair 64
   int seg_tiles, n_segs, cap;       // id-segment length (tiles), segments per CTA, candidate slots per query
   int64_t tau_off, outs_off, outi_off, outn_off, samp_off, cnt_off, total;
 };
 
 MmaPlan mma_plan(int B, int64_t N) {
   MmaPlan p;
-  p.n_qt = ceil_div(B, SM_MQ);
+  const int n_qt = ceil_div(B, SM_MQ);
+  p.pair = n_qt >= 2 && !(g_debug_flags & (1 << 27));      // debug bit 27: one CTA per query tile as in round 1 (A/B)
+  p.n_qt = p.pair ? (n_qt + 1) / 2 * 2 : n_qt;              // grid.x: a pair needs two tiles (the odd one out has no valid query)
+  p.nd_t = p.pair ? 2 * SM_ND : SM_ND;
   const int sms = sm_count();
   p.n_slices = std::max(1, sms / p.n_qt);      // one wave: n_qt * n_slices <= #SMs (1 CTA per SM)
   p.n_ctas = p.n_qt * p.n_slices;
-  // a list entry numbers its document with 16 bits inside a segment of <= 2048 tiles; the CTA publishes its list at
+  // a list entry numbers its document with 16 bits inside a segment of <= 65536 documents; the CTA publishes its list at
   // every segment boundary (debug bit 24: 16-tile segments, so small test corpora cross many boundaries)
-  p.seg_tiles = (g_debug_flags & (1 << 24)) ? 16 : SM_MAX_TILES_PER_CTA;
-  const int64_t n_tiles = ceil_div64(N, (int64_t)SM_ND);
+  p.seg_tiles = (g_debug_flags & (1 << 24)) ? 16 : 65536 / p.nd_t;
+  const int64_t n_tiles = ceil_div64(N, (int64_t)p.nd_t);
   p.n_segs = (int)std::max<int64_t>(1, ceil_div64(ceil_div64(n_tiles, (int64_t)p.n_slices), (int64_t)p.seg_tiles));
   p.cap = p.n_slices * p.n_segs * SM_KEEP;
   auto align = [](int64_t v) { return (v + 255) / 256 * 256; };
@@ -898,6 +957,35 @@ MmaPlan mma_plan(int B, int64_t N) {
   p.cnt_off = align(p.samp_off + bp * p.n_slices * SM_SAMPLE_TOP * 4);
   p.total = align(p.cnt_off + 16);
   return p;
+}
+
+// One launch path for the six instantiations: cluster dimension (2,1,1) for pairs, cooperative for the fused mode.
+static cudaError_t launch_scorer(const void* kern, dim3 grid, size_t smem, cudaStream_t st, bool pair, bool coop, void** args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(SM_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[2];
+  int n = 0;
+  if (pair) {
+    at[n].id = cudaLaunchAttributeClusterDimension;
+    at[n].val.clusterDim.x = 2; at[n].val.clusterDim.y = 1; at[n].val.clusterDim.z = 1;
+    ++n;
+  }
+  if (coop) {
+    at[n].id = cudaLaunchAttributeCooperative;
+    at[n].val.cooperative = 1;
+    ++n;
+  }
+  cfg.attrs = at;
+  cfg.numAttrs = n;
+  return cudaLaunchKernelExC(&cfg, kern, args);
+}
+
+template <int MODE>
+static const void* scorer_fn(bool pair) {
+  return pair ? (const void*)score_topk_mma_kernel<MODE, true> : (const void*)score_topk_mma_kernel<MODE, false>;
 }
 
 int launch_score_topk_mma(const float* Q, int B, const float* docs, int64_t N, int k, int64_t row_offset,
@@ -918,12 +1006,21 @@ int launch_score_topk_mma(const float* Q, int B, const float* docs, int64_t N, i
   int cur_dev = 0;
   TTR_CHECK_CUDA(cudaGetDevice(&cur_dev));
   if (attr_dev != cur_dev) {
-    TTR_CHECK_CUDA(cudaFuncSetAttribute(score_topk_mma_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    TTR_CHECK_CUDA(cudaFuncSetAttribute(score_topk_mma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    TTR_CHECK_CUDA(cudaFuncSetAttribute(score_topk_mma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    for (int pr = 0; pr < 2; ++pr) {
+      TTR_CHECK_CUDA(cudaFuncSetAttribute(scorer_fn<0>(pr), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      TTR_CHECK_CUDA(cudaFuncSetAttribute(scorer_fn<1>(pr), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      TTR_CHECK_CUDA(cudaFuncSetAttribute(scorer_fn<2>(pr), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
     attr_dev = cur_dev;
   }
-  const FusedArgs no_fuse{nullptr, nullptr, 0};
+  FusedArgs fa{nullptr, nullptr, 0};
+  long long* tr = nullptr;
+  int dbgv = g_debug_flags;
+  CUtensorMap map;
+  int64_t n_scan = N;
+  int n_sl = p.n_slices, seg = p.seg_tiles, cap = p.cap;
+  void* args[] = {(void*)&Q, (void*)&map, (void*)&B, (void*)&n_scan, (void*)&k, (void*)&n_sl, (void*)&tau, (void*)&outs,
+                  (void*)&outi, (void*)&outn, (void*)&tr, (void*)&dbgv, (void*)&fa, (void*)&seg, (void*)&cap};
   // Sample pass: exact top-k of the first ~38 k documents gives every query a k-th-best bound
   // (top ~0.1 %) before the full scan starts.  Without it each CTA spends its first ~250
   // tiles appending and compacting almost everything it sees (3-4 k cycles per tile instead
@@ -942,52 +1039,43 @@ int launch_score_topk_mma(const float* Q, int B, const float* docs, int64_t N, i
   // scan >= 8 k tiles each, the ~250-tile transient is noise there).
   const bool sample_useful = p.n_slices * SM_SAMPLE_TOP >= 3 * k;
   // all CTAs co-resident (one wave): sample phase, bound selection and main pass in ONE cooperative launch
-  static int fused_ok[64];                    // per device: 0 unknown, 1 works, -1 the device refused the cooperative launch
+  static int fused_ok[64][2];                 // per device and kernel flavour: 0 unknown, 1 works, -1 refused once
   // (measured: 0.263 vs 0.274 ms per 128-query step on a 1.1 M-document shard, no difference on 8.8 M documents,
   // where the two-pass path stays the default; debug bit 22 forces the fused launch there too)
   const bool fuse_size = N < 4000000 || (g_debug_flags & (1 << 22));
   if (N >= 16 * n_sample && sample_useful && !(g_debug_flags & (256 | (1 << 21))) && p.n_ctas <= sm_count() &&
-      fused_ok[cur_dev & 63] >= 0 && fuse_size) {
-    CUtensorMap map_f;
-    int rcf = make_tf32_rowmajor_map(&map_f, docs, N, SM_DIM, SM_ND);
+      fused_ok[cur_dev & 63][p.pair] >= 0 && fuse_size) {
+    int rcf = make_tf32_rowmajor_map(&map, docs, N, SM_DIM, SM_ND);
     if (rcf != TTR_OK) return rcf;
     // every query sees the same number of sample documents whatever the slice count
-    FusedArgs fa{samp, counters, (int)ceil_div64(n_sample / SM_ND, (int64_t)p.n_slices)};
-    long long* tr = g_score_trace;
-    int dbgv = g_debug_flags;
-    int n_sl = p.n_slices, seg = p.seg_tiles, cap = p.cap;
-    void* args[] = {(void*)&Q, (void*)&map_f, (void*)&B, (void*)&N, (void*)&k, (void*)&n_sl, (void*)&tau, (void*)&outs,
-                    (void*)&outi, (void*)&outn, (void*)&tr, (void*)&dbgv, (void*)&fa, (void*)&seg, (void*)&cap};
-    cudaError_t ce = cudaLaunchCooperativeKernel((const void*)score_topk_mma_kernel<2>, dim3(p.n_qt, p.n_slices),
-                                                 dim3(SM_THREADS), args, smem, st);
+    fa = FusedArgs{samp, counters, (int)ceil_div64(n_sample / p.nd_t, (int64_t)p.n_slices)};
+    tr = g_score_trace;
+    cudaError_t ce = launch_scorer(scorer_fn<2>(p.pair), dim3(p.n_qt, p.n_slices), smem, st, p.pair, true, args);
     if (ce == cudaSuccess) {
-      fused_ok[cur_dev & 63] = 1;
+      fused_ok[cur_dev & 63][p.pair] = 1;
       return launch_select_merge(outs, outi, outn, B, p.cap, k, row_offset, out_scores, out_idx, st);
     }
     (void)cudaGetLastError();                 // not co-resident on this device/partition: use the two-pass path
-    fused_ok[cur_dev & 63] = -1;
+    fused_ok[cur_dev & 63][p.pair] = -1;
+    fa = FusedArgs{nullptr, nullptr, 0};
+    tr = nullptr;
   }
   if (N >= 16 * n_sample && sample_useful && !(g_debug_flags & 256)) {
     MmaPlan ps = mma_plan(B, n_sample);
-    CUtensorMap map_s;
-    int rc = make_tf32_rowmajor_map(&map_s, docs, n_sample, SM_DIM, SM_ND);
+    int rc = make_tf32_rowmajor_map(&map, docs, n_sample, SM_DIM, SM_ND);
     if (rc != TTR_OK) return rc;
-    dim3 gs(ps.n_qt, ps.n_slices);
-    score_topk_mma_kernel<1><<<gs, SM_THREADS, smem, st>>>(Q, map_s, B, n_sample, k, ps.n_slices, tau, outs, outi,
-                                                          outn, nullptr, g_debug_flags, no_fuse, ps.seg_tiles, ps.cap);
-    TTR_CHECK_LAUNCH();
+    n_scan = n_sample; n_sl = ps.n_slices; seg = ps.seg_tiles; cap = ps.cap;
+    TTR_CHECK_CUDA(launch_scorer(scorer_fn<1>(ps.pair), dim3(ps.n_qt, ps.n_slices), smem, st, ps.pair, false, args));
     rc = launch_select_merge(outs, outi, outn, B, ps.cap, k, 0, out_scores, out_idx, st);
     if (rc != TTR_OK) return rc;
     seed_tau_kernel<<<ceil_div(nq_pad, 256), 256, 0, st>>>(tau, outn, out_scores, out_idx, B, nq_pad, k);
     TTR_CHECK_LAUNCH();
   }
-  CUtensorMap map_d;
-  int rc = make_tf32_rowmajor_map(&map_d, docs, N, SM_DIM, SM_ND);
+  int rc = make_tf32_rowmajor_map(&map, docs, N, SM_DIM, SM_ND);
   if (rc != TTR_OK) return rc;
-  dim3 grid(p.n_qt, p.n_slices);
-  score_topk_mma_kernel<0><<<grid, SM_THREADS, smem, st>>>(Q, map_d, B, N, k, p.n_slices, tau, outs, outi, outn,
-                                                           g_score_trace, g_debug_flags, no_fuse, p.seg_tiles, p.cap);
-  TTR_CHECK_LAUNCH();
+  n_scan = N; n_sl = p.n_slices; seg = p.seg_tiles; cap = p.cap;
+  tr = g_score_trace;
+  TTR_CHECK_CUDA(launch_scorer(scorer_fn<0>(p.pair), dim3(p.n_qt, p.n_slices), smem, st, p.pair, false, args));
   return launch_select_merge(outs, outi, outn, B, p.cap, k, row_offset, out_scores, out_idx, st);
 }
 
