@@ -173,7 +173,10 @@ int ttr_positive_rank(const float* Q, const float* docs, const int64_t* target, 
  * bits12-17 = sample tiles per SM override, bit20 = per-CTA entry/exit times into the trace buffer,
  * bit21 = never fuse the sample pass into the main scorer launch, bit22 = always fuse it,
  * bit24 = 16-tile id segments in the tcgen05 scorer (tests cross many segment boundaries on small corpora),
- * bit25 = scorer epilogue without the max-tree fast reject (A/B timing). */
+ * bit25 = scorer epilogue without the max-tree fast reject (A/B timing),
+ * bit26 = CTA-pair scorer: swap which CTA loads which half of a 64-document tile (bring-up switch; breaks results),
+ * bit27 = one CTA per query tile for B > 128 (the round-1 layout) instead of CTA pairs,
+ * bit28 = CTA-pair scorer: cta_group::2 TMA loads counted on the leader's barrier instead of plain loads + forwarding. */
 int ttr_debug_set_flags(int flags);
 int ttr_debug_get_flags(int* out);
 /* Diagnostic: number of 8-CTA clusters of the tcgen05 recurrence the device holds at once. */

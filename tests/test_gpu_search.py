@@ -245,7 +245,7 @@ def test_headline_corpus_8p8M_docs(cuda_device, B, n_check):
     assert torch.equal(i, i2) and torch.equal(s, s2)
 
 
-@pytest.mark.parametrize("B,N", [(128, 300_000), (256, 300_000), (300, 150_000), (1024, 100_000), (40, 70_001), (129, 33),
+@pytest.mark.parametrize("B,N", [(128, 300_000), (256, 300_000), (300, 150_000), (1024, 100_000), (40, 70_001), (129, 3333),
                                  (512, 1_000_003)])
 def test_id_segments_and_fast_reject(cuda_device, B, N):
     """B > 128 runs CTA PAIRS (tcgen05.mma.cta_group::2, 64-document tiles, each CTA loads half of every tile).
@@ -255,7 +255,7 @@ def test_id_segments_and_fast_reject(cuda_device, B, N):
     two-pass path, and to the epilogue without the max-tree fast reject (bit 25)."""
     from twotowermlretrieval_b200 import _lib
     D = torch.tensor(synth.make_unit_rows(N, 256, seed=70 + B), device=cuda_device)
-    D[N // 2:N // 2 + 300] = D[100:400]                       # exact ties across slices and segments
+    D[N // 2:N // 2 + 300] = D[100:400].clone()               # exact ties across slices and segments
     Q = torch.tensor(synth.make_unit_rows(B, 256, seed=80 + B), device=cuda_device)
     s_a, i_a = search_topk(Q, D, 50)
     # bit 27: one CTA per query tile (round-1 layout) instead of CTA pairs for B > 128

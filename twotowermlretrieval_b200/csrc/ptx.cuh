@@ -203,8 +203,12 @@ __device__ __forceinline__ uint32_t mapa(uint32_t smem_addr, uint32_t rank) {
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(d) : "r"(smem_addr), "r"(rank));
   return d;
 }
+// Remote arrive WITHOUT cluster-scope release: `.release.cluster` compiles to MEMBAR.ALL.GPU + ERRBAR + CGAERRBAR in
+// front of the arrive (r2 ncu: the peer CTA's epilogue spent its time in those, and the pair ran at half speed).  The
+// callers only order tcgen05 / TMA (async-proxy) work, which tcgen05.wait + tcgen05.fence::before_thread_sync or the
+// mbarrier phase they waited on already completed; this is the form CUTLASS's ClusterBarrier::arrive(cta_id) emits.
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ void tmem_alloc_2cta(uint32_t* smem_result, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)),

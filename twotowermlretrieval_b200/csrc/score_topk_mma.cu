@@ -320,6 +320,12 @@ scorer_body(const float* __restrict__ Q, const CUtensorMap& map_d, int B, int64_
   // which 32 documents of a 64-document pair tile this CTA loads: B rows [0, 32) come from rank 0's shared memory,
   // rows [32, 64) from rank 1's (debug bit 26 swaps the assignment: bring-up switch for that convention)
   const int my_half = PAIR ? (int)(cta_rank ^ ((dbg >> 26) & 1u)) : 0;
+  // How the leader learns that the PEER's half of a stage has landed.  Default: every CTA loads with the plain TMA form
+  // onto its OWN `full` barrier and the peer's otherwise idle warp 1 forwards each completion with a remote arrive on the
+  // leader's `peer_full` barrier.  Debug bit 28: the cta_group::2 TMA form counting both CTAs' bytes on the leader's
+  // barrier — measured 2.6x slower (r2 traces: 7-9 k cycles per 32 KB stage at half the HBM rate, against 2.9 k with plain
+  // loads), so it is kept only as the A/B switch.
+  const bool tma_2cta = PAIR && (dbg & (1 << 28));
   extern __shared__ unsigned char smem_raw[];
   unsigned char* base = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
   unsigned char* ring = base;                                      // [stages][SM_KB][32 rows][128 B]
@@ -329,7 +335,8 @@ scorer_body(const float* __restrict__ Q, const CUtensorMap& map_d, int B, int64_
   uint64_t* empty_bar = full_bar + SM_STAGES;
   uint64_t* acc_full = empty_bar + SM_STAGES;
   uint64_t* acc_empty = acc_full + SM_NACC;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + SM_NACC);
+  uint64_t* peer_full = acc_empty + SM_NACC;       // pair, leader only: "the peer's half of stage s has landed"
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(peer_full + SM_STAGES);
   __shared__ uint64_t probe_bar;             // dbg & 64: the MMA warp waits for its own commit (timing experiment)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -355,7 +362,9 @@ scorer_body(const float* __restrict__ Q, const CUtensorMap& map_d, int B, int64_
   auto tile_at = [&](int it) -> int64_t { return (int64_t)slice + (int64_t)(it < S ? it : it - S) * n_slices; };
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < SM_STAGES; ++s) { ptx::mbar_init(full_bar + s, 1); ptx::mbar_init(empty_bar + s, 1); }
+    for (int s = 0; s < SM_STAGES; ++s) {
+      ptx::mbar_init(full_bar + s, 1); ptx::mbar_init(empty_bar + s, 1); ptx::mbar_init(peer_full + s, 1);
+    }
     // accumulator release: the four epilogue warps of this CTA (+ the four of the peer, on the leader's barrier)
     for (int b = 0; b < SM_NACC; ++b) { ptx::mbar_init(acc_full + b, 1); ptx::mbar_init(acc_empty + b, PAIR ? 8 : 4); }
     ptx::mbar_init(&probe_bar, 1);
@@ -416,7 +425,7 @@ scorer_body(const float* __restrict__ Q, const CUtensorMap& map_d, int B, int64_
       unsigned char* dst = ring + s * SM_STAGE_BYTES;
       const int32_t d0 = (int32_t)(t * ND_T) + my_half * SM_ND;
       if (ptx::elect_one()) {
-        if (PAIR) {
+        if (tma_2cta) {
           // both CTAs' bytes are counted on the LEADER's barrier (one arrival: the leader's expect_tx for 2 x 32 KB; a
           // peer load that lands first only drives the transaction count negative until then)
           if (leader) ptx::mbar_arrive_expect_tx(full_bar + s, 2 * SM_STAGE_BYTES);
@@ -445,6 +454,7 @@ scorer_body(const float* __restrict__ Q, const CUtensorMap& map_d, int B, int64_
       const uint32_t aph = (uint32_t)(it / SM_NACC) & 1u;
       ptx::mbar_wait(acc_empty + buf, aph ^ 1u);
       ptx::mbar_wait(full_bar + s, ph);
+      if (PAIR && !tma_2cta) ptx::mbar_wait(peer_full + s, ph);
       ptx::tc_fence_after_sync();
       SM_TRACE(1, it);
       const uint32_t d_addr = ptx::smem_u32(ring + ((dbg & 16) ? 0 : s) * SM_STAGE_BYTES);
@@ -481,6 +491,15 @@ scorer_body(const float* __restrict__ Q, const CUtensorMap& map_d, int B, int64_
         ptx::mbar_wait(&probe_bar, (uint32_t)it & 1u);
         SM_TRACE(5, it);
       }
+    }
+  } else if (PAIR && warp == 1 && !tma_2cta) {
+    // ===== peer CTA: forward "my half of stage s has landed" to the leader's MMA issuer =====
+    for (int it = 0; it < n_seq; ++it) {
+      const int s = it % SM_STAGES;
+      const uint32_t ph = (uint32_t)(it / SM_STAGES) & 1u;
+      ptx::mbar_wait(full_bar + s, ph);
+      if (ptx::elect_one()) ptx::mbar_arrive_cluster(ptx::mapa(ptx::smem_u32(peer_full + s), 0u));
+      __syncwarp();
     }
   } else if (warp >= 4) {
     // ===== epilogue: one thread per query =====
@@ -1001,7 +1020,7 @@ int launch_score_topk_mma(const float* Q, int B, const float* docs, int64_t N, i
   unsigned int* counters = reinterpret_cast<unsigned int*>(ws + p.cnt_off);
   init_tau_kernel<<<ceil_div(nq_pad, 256), 256, 0, st>>>(tau, outn, nq_pad, counters);
   TTR_CHECK_LAUNCH();
-  const size_t smem = (size_t)SM_STAGES * SM_STAGE_BYTES + SM_LIST_BYTES + SM_LISTI_BYTES + (2 * SM_STAGES + 2 * SM_NACC) * 8 + 16 + 1024;
+  const size_t smem = (size_t)SM_STAGES * SM_STAGE_BYTES + SM_LIST_BYTES + SM_LISTI_BYTES + (3 * SM_STAGES + 2 * SM_NACC) * 8 + 16 + 1024;
   static thread_local int attr_dev = -1;
   int cur_dev = 0;
   TTR_CHECK_CUDA(cudaGetDevice(&cur_dev));
