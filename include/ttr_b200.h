@@ -164,6 +164,11 @@ int ttr_colsum(const float* A, int m_bound, const int32_t* m_valid, int N, float
  * receives s_qt. */
 int ttr_positive_rank(const float* Q, const float* docs, const int64_t* target, int B, int64_t N, int D,
                       int32_t* rank_out, float* score_out, void* stream);
+/* HOST helper (no device work, no stream): ragged token rows -> right-padded [n_rows, T] int64, zero fill —
+ * `pad_sequence(batch_first=True, padding_value=0)` of the reference collate (backend/main.py:50-56) — written into
+ * a caller-owned (pinned) buffer; output row r = ragged row rows[r] (flat ids, start offsets, lengths). */
+int ttr_pack_padded_i64(const int64_t* flat, const int64_t* starts, const int64_t* lengths,
+                        const int64_t* rows, int64_t n_rows, int64_t T, int64_t* out);
 /* Test/debug switches: bit0 = force the generic (any-H) GRU kernels, bit1 = encode TMA maps
  * as FLOAT32 instead of TFLOAT32 (hardware truncation instead of round-to-nearest),
  * bit2 = force the CUDA-core streaming scorer for every batch size, bit8 = no sample pass,
@@ -176,7 +181,8 @@ int ttr_positive_rank(const float* Q, const float* docs, const int64_t* target, 
  * bit25 = scorer epilogue without the max-tree fast reject (A/B timing),
  * bit26 = CTA-pair scorer: swap which CTA loads which half of a 64-document tile (bring-up switch; breaks results),
  * bit27 = one CTA per query tile for B > 128 (the round-1 layout) instead of CTA pairs,
- * bit28 = CTA-pair scorer: cta_group::2 TMA loads counted on the leader's barrier instead of plain loads + forwarding. */
+ * bit28 = CTA-pair scorer: cta_group::2 TMA loads counted on the leader's barrier instead of plain loads + forwarding,
+ * bit29 = tcgen05 scorer without the screening warps (every tile goes through the list-keeping warps, as in round 1). */
 int ttr_debug_set_flags(int flags);
 int ttr_debug_get_flags(int* out);
 /* Diagnostic: number of 8-CTA clusters of the tcgen05 recurrence the device holds at once. */

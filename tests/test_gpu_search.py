@@ -259,7 +259,8 @@ def test_id_segments_and_fast_reject(cuda_device, B, N):
     Q = torch.tensor(synth.make_unit_rows(B, 256, seed=80 + B), device=cuda_device)
     s_a, i_a = search_topk(Q, D, 50)
     # bit 27: one CTA per query tile (round-1 layout) instead of CTA pairs for B > 128
-    for flags in (1 << 24, (1 << 24) | (1 << 21), 1 << 25, (1 << 24) | (1 << 25), 1 << 21, 1 << 27, (1 << 27) | (1 << 24)):
+    for flags in (1 << 24, (1 << 24) | (1 << 21), 1 << 25, (1 << 24) | (1 << 25), 1 << 21, 1 << 27, (1 << 27) | (1 << 24),
+                  1 << 29, (1 << 29) | (1 << 24), (1 << 29) | (1 << 21)):     # bit 29: no screening warps
         _lib.call_nostream("ttr_debug_set_flags", flags)
         try:
             s_b, i_b = search_topk(Q, D, 50)

@@ -182,3 +182,104 @@ def test_corpus_artifact_reader_formats_and_errors(tmp_path):
         load_corpus_artifacts(tmp_path / "nope")
     p = pad_rows([[1, 2, 3], [], [7]])
     assert p.dtype == torch.int64 and p.tolist() == [[1, 2, 3], [0, 0, 0], [7, 0, 0]]
+
+
+def _gloo_worker2(rank, world, port, q):
+    """Host-side N > 1 logic on CPU: (a) the peer-exchange decision is AGREED across ranks — a rank whose symmetric
+    allocation fails takes every rank to the all-gather path instead of splitting the group (ADVICE r1);
+    (b) differing batch sizes raise on every rank; (c) bench.py's verifier (fp64 top-k over all shards,
+    rank-identity check) agrees with the unsharded oracle."""
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    out = {}
+    try:
+        from twotowermlretrieval_b200 import _lib, index as ix
+
+        class Boom:
+            def __init__(self, group, device, max_b, k):
+                if dist.get_rank() == 1:
+                    raise RuntimeError("no P2P mapping on this rank")
+                self.k, self.max_b = k, max_b
+
+        real = ix._PeerExchange
+        ix._PeerExchange = Boom
+        try:
+            idx = ix.ShardedIndex.__new__(ix.ShardedIndex)
+            idx.docs = torch.zeros(4, 256)
+            idx.group, idx._dist, idx.world, idx.rank = None, dist, world, rank
+            idx.peer_memory, idx._px = True, None
+            import warnings
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                out["agreed_fallback"] = idx._exchange(8, 50) is None and idx.peer_memory is False
+            idx.peer_memory, idx._px = True, None
+            try:
+                idx._exchange(8 + rank, 50)          # B differs across ranks
+                out["mismatch_raises"] = False
+            except _lib.TTRError:
+                out["mismatch_raises"] = True
+        finally:
+            ix._PeerExchange = real
+        # (c) the bench verifier on CPU tensors
+        import bench
+        c = bench.Ctx()
+        c.world, c.rank, c.dist, c.dev = world, rank, dist, torch.device("cpu")
+        D = torch.tensor(synth.make_unit_rows(5003, 256, seed=3))
+        Q = torch.tensor(synth.make_unit_rows(4, 256, seed=4))
+        lo, hi = shard_bounds(D.shape[0], world, rank)
+        s, i = bench.fp64_topk_all_shards(c, Q, D[lo:hi], lo, 50)
+        fs, fi = onp.cosine_topk(Q.numpy(), D.numpy(), 50, dtype=np.float64)
+        out["verifier_topk"] = bool((i.numpy() == fi).all()) and float(np.abs(s.numpy() - fs).max()) < 1e-12
+        good = bench.check_against_fp64(c, Q, s.float(), i, D[lo:hi], lo, 50)
+        bad_i = i.clone()
+        bad_i[0, 3] = (bad_i[0, 3] + 7) % 5003       # a wrong document must be caught
+        bad = bench.check_against_fp64(c, Q, s.float(), bad_i, D[lo:hi], lo, 50)
+        out["verifier_accepts"], out["verifier_rejects"] = good["ok"], not bad["ok"]
+        out["same_true"] = bench.same_on_all_ranks(c, i)
+        out["same_false"] = not bench.same_on_all_ranks(c, i + rank)
+        q.put((rank, out))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_gloo_exchange_agreement_and_bench_verifier():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_gloo_worker2, args=(r, 2, port, q)) for r in range(2)]
+    [p.start() for p in procs]
+    res = dict(q.get(timeout=300) for _ in range(2))
+    [p.join(60) for p in procs]
+    for rank in (0, 1):
+        assert all(res[rank].values()), (rank, res[rank])
+
+
+def test_host_packer_matches_pad_sequence():
+    """`ttr_pack_padded_i64` (host C helper of encode_rows) == `pad_sequence(batch_first=True, padding_value=0)`
+    (backend/main.py:50-56) on the selected rows."""
+    from twotowermlretrieval_b200 import _lib
+    rng = np.random.default_rng(3)
+    lengths = rng.integers(1, 40, size=200).astype(np.int64)
+    flat = rng.integers(1, 1000, size=int(lengths.sum())).astype(np.int64)
+    starts = np.zeros(201, dtype=np.int64)
+    np.cumsum(lengths, out=starts[1:])
+    rows = np.ascontiguousarray(np.argsort(-lengths, kind="stable")[:64].astype(np.int64))
+    T = int(lengths[rows[0]])
+    out = torch.full((64, T), -1, dtype=torch.int64)
+    _lib.call_nostream("ttr_pack_padded_i64", flat.ctypes.data, starts.ctypes.data, lengths.ctypes.data, rows.ctypes.data,
+                       64, T, out.data_ptr())
+    ref = torch.nn.utils.rnn.pad_sequence([torch.tensor(flat[starts[r]:starts[r] + lengths[r]]) for r in rows],
+                                          batch_first=True, padding_value=0)
+    assert torch.equal(out, ref)
+
+
+def test_plan_batches_rounds_rows_to_whole_recurrence_waves():
+    from twotowermlretrieval_b200.encode import ROW_QUANTUM
+    rng = np.random.default_rng(1)
+    lengths = synth.make_lengths(60000, "passage", rng)
+    order, bounds = plan_batches(lengths, max_tokens=524288, max_rows=15360)
+    assert bounds[0][0] == 0 and bounds[-1][1] == 60000
+    for lo, hi in bounds[:-1]:
+        assert (hi - lo) % ROW_QUANTUM == 0 or hi - lo < ROW_QUANTUM

@@ -1,5 +1,6 @@
 // runtime.cu — thread-local error text and device queries.
 #include <stdarg.h>
+#include <string.h>
 
 #include "common.cuh"
 
@@ -38,5 +39,22 @@ extern "C" int ttr_sm_count(int* out_h) {
   TTR_CHECK_CUDA(cudaGetDeviceProperties(&prop, dev));
   TTR_REQUIRE(prop.major == 10, "ttr_b200 needs an sm_100 device, found sm_%d%d", prop.major, prop.minor);
   *out_h = prop.multiProcessorCount;
+  return TTR_OK;
+}
+
+// HOST helper of the input pipeline (no device work): ragged token rows -> one right-padded [n_rows, T] int64 matrix
+// (`pad_sequence(batch_first=True, padding_value=0)`, backend/main.py:50-56) written straight into a pinned staging
+// buffer.  Row r of the output is row rows[r] of the ragged set (flat ids + start offsets + lengths).
+extern "C" int ttr_pack_padded_i64(const int64_t* flat, const int64_t* starts, const int64_t* lengths,
+                                   const int64_t* rows, int64_t n_rows, int64_t T, int64_t* out) {
+  TTR_REQUIRE(flat && starts && lengths && rows && out && n_rows >= 0 && T >= 0, "ttr_pack_padded_i64: bad arguments");
+  for (int64_t r = 0; r < n_rows; ++r) {
+    const int64_t src = rows[r];
+    int64_t len = lengths[src];
+    if (len > T) len = T;
+    int64_t* dst = out + r * T;
+    memcpy(dst, flat + starts[src], (size_t)len * sizeof(int64_t));
+    memset(dst + len, 0, (size_t)(T - len) * sizeof(int64_t));
+  }
   return TTR_OK;
 }

@@ -50,7 +50,8 @@ constexpr int SM_KSPLIT = 1;                            // accumulation chains p
 constexpr int SM_ACC_COLS = SM_KSPLIT * SM_ND;          // columns per buffer: partial sums x 32 docs
 constexpr int SM_Q_COLS = SM_DIM;                       // A operand: one column per k element
 constexpr int SM_TMEM_COLS = 512;
-constexpr int SM_THREADS = 256;
+constexpr int SM_THREADS = 384;                         // warps: 0 TMA, 1 MMA (peer: forwarder), 2 TMEM alloc, 3 idle,
+                                                        // 4-7 keepers (one thread per query), 8-11 screeners (ditto)
 constexpr int SM_CAP = 128;                             // candidate slots per query
 constexpr int SM_KEEP = 64;                             // a compaction leaves k..SM_KEEP entries
 constexpr int SM_LIST_BYTES = SM_CAP * SM_MQ * 4;       // score lists ([slot][thread]): 64 KB
@@ -338,6 +339,20 @@ scorer_body(const float* __restrict__ Q, const CUtensorMap& map_d, int B, int64_
   uint64_t* peer_full = acc_empty + SM_NACC;       // pair, leader only: "the peer's half of stage s has landed"
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(peer_full + SM_STAGES);
   __shared__ uint64_t probe_bar;             // dbg & 64: the MMA warp waits for its own commit (timing experiment)
+  // Screening (default; debug bit 29 switches it off).  The epilogue used to be ONE warp per scheduler doing everything
+  // for its 32 queries: wait, tcgen05.ld, filter, list upkeep — a ~1,500-cycle dependent chain per 64-document tile
+  // that nothing overlapped, the bound of every batch above 128 queries once the CTA pairs had fixed the operand feed.
+  // Now a second warp per lane quarter (a "screener", warps 8-11) reads every accumulator first, reduces the thread's
+  // scores to their maximum and votes against the queries' current thresholds; tiles in which no query of the quarter
+  // has a survivor (~3 of 4 once the bounds are seeded) are released right there.  Only the others are queued for the
+  // quarter's "keeper" warp (4-7), which owns the candidate lists and runs the unchanged filter / compaction code on
+  // them, in tile order.  Thresholds flow keeper -> screener through `thr_sh` (stale = looser = safe).
+  __shared__ float thr_sh[SM_MQ];            // per query: a score below this cannot enter the list
+  __shared__ int hit_q[4][8];                // per lane quarter: tiles the keeper must process (<= SM_NACC pending)
+  __shared__ int hit_wr[4];                  // entries written to hit_q
+  __shared__ int scr_tiles[4];               // tiles the screener has classified
+  __shared__ int go_main[4];                 // fused launch: the keeper has published the seeded bounds
+  const bool screen_on = !(dbg & (1 << 29));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 #define SM_MARK(slot)                                                                                   \
@@ -369,6 +384,7 @@ scorer_body(const float* __restrict__ Q, const CUtensorMap& map_d, int B, int64_
     for (int b = 0; b < SM_NACC; ++b) { ptx::mbar_init(acc_full + b, 1); ptx::mbar_init(acc_empty + b, PAIR ? 8 : 4); }
     ptx::mbar_init(&probe_bar, 1);
     ptx::fence_mbar_init();
+    for (int w = 0; w < 4; ++w) { hit_wr[w] = 0; scr_tiles[w] = 0; go_main[w] = 0; }
   }
   if (warp == 2) {
     if (PAIR) { ptx::tmem_alloc_2cta(tmem_slot, SM_TMEM_COLS); ptx::tmem_relinquish_2cta(); }
@@ -381,9 +397,12 @@ scorer_body(const float* __restrict__ Q, const CUtensorMap& map_d, int B, int64_
   const uint32_t tmem_acc = tmem_base + SM_Q_COLS;
 
   // ---- stage the query tile into tensor memory: thread (warp 4+w, lane) owns TMEM lane 32w+lane
-  if (warp >= 4) {
+  if (warp >= 4 && warp < 8) {
     const int qw = warp - 4;
     const int q = q0 + qw * 32 + lane;
+    // initial screening threshold: the seeded global bound (main pass), "anything" while a sample top-4 is empty,
+    // +inf for the padding queries of the last tile
+    thr_sh[qw * 32 + lane] = q >= B ? INFINITY : (MODE == 0 ? __ldcg(tau_g + q) : -3.402823466e38f);
     const float4* src = reinterpret_cast<const float4*>(Q + (int64_t)(q < B ? q : 0) * SM_DIM);
     // two round trips of 32 independent 16-byte loads each (the row is 1 KB; eight dependent
     // round trips of 8 loads cost ~8 us of the ~30 us fixed cost of a launch)
@@ -501,8 +520,83 @@ scorer_body(const float* __restrict__ Q, const CUtensorMap& map_d, int B, int64_
       if (ptx::elect_one()) ptx::mbar_arrive_cluster(ptx::mapa(ptx::smem_u32(peer_full + s), 0u));
       __syncwarp();
     }
+  } else if (warp >= 8) {
+    // ===== screener: one thread per query; classifies every tile, releases the ones without a survivor =====
+    const int qw = warp - 8;
+    const int ql = qw * 32 + lane;
+    const int q = q0 + ql;
+    const bool q_valid = q < B;
+    volatile float* thr_v = thr_sh;
+    volatile int* hit_wr_v = hit_wr;
+    volatile int* scr_v = scr_tiles;
+    volatile int* go_v = go_main;
+    float tgp = (q_valid && MODE == 0) ? __ldcg(tau_g + q) : (q_valid ? -INFINITY : INFINITY);
+    float tgp_pending = tgp;
+    int wr = 0;
+    for (int it = 0; screen_on && it < n_seq; ++it) {
+      if (FUSED && it == S) {
+        // the keeper publishes the seeded bounds after the grid barriers; main tiles must not be judged by the
+        // sample thresholds (those say "beats my 4th best", not "can be in the top k")
+        for (unsigned spin = 0; go_v[qw] == 0; ++spin) {
+          __nanosleep(64);
+          if (spin > (1u << 26)) __trap();
+        }
+        tgp = q_valid ? __ldcg(tau_g + q) : INFINITY;
+        tgp_pending = tgp;
+      }
+      const bool smp = SAMPLE || (FUSED && it < S);
+      if ((it & 7) == 0 && q_valid && !smp) {
+        tgp = fmaxf(tgp, tgp_pending);
+        tgp_pending = __ldcg(tau_g + q);
+      }
+      const int64_t t = tile_at(it);
+      const int buf = it % SM_NACC;
+      ptx::mbar_wait(acc_full + buf, (uint32_t)(it / SM_NACC) & 1u);
+      ptx::tc_fence_after_sync();
+      float mx = -INFINITY;
+      {
+        const uint32_t tcol = tmem_acc + ((uint32_t)(qw * 32) << 16) + buf * ND_T;
+        uint32_t r[HALVES][32];
+#pragma unroll
+        for (int h = 0; h < HALVES; ++h) ptx::tmem_ld_32x32(tcol + h * SM_ND, r[h]);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int h = 0; h < HALVES; ++h) {
+          float m16[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) m16[j] = fmaxf(__uint_as_float(r[h][2 * j]), __uint_as_float(r[h][2 * j + 1]));
+#pragma unroll
+          for (int w = 8; w > 0; w >>= 1)
+#pragma unroll
+            for (int j = 0; j < w; ++j) m16[j] = fmaxf(m16[j], m16[j + w]);
+          mx = fmaxf(mx, m16[0]);
+        }
+      }
+      const float thr = fmaxf(thr_v[ql], smp ? -INFINITY : tgp);
+      // the last tile holds zero-filled rows beyond N: the keeper masks them, so it always gets that tile
+      const bool hit = __any_sync(0xffffffffu, mx >= thr) || (t + 1) * ND_T > N;
+      if (!hit) {
+        ptx::tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) {
+          if (!PAIR || leader) ptx::mbar_arrive(acc_empty + buf);
+          else ptx::mbar_arrive_cluster(ptx::mapa(ptx::smem_u32(acc_empty + buf), 0u));
+        }
+      } else {
+        if (lane == 0) {
+          hit_q[qw][wr & 7] = it;
+          __threadfence_block();
+          hit_wr_v[qw] = wr + 1;
+        }
+        ++wr;
+      }
+      if (lane == 0) {
+        __threadfence_block();
+        scr_v[qw] = it + 1;
+      }
+    }
   } else if (warp >= 4) {
-    // ===== epilogue: one thread per query =====
+    // ===== keeper: one thread per query; owns the candidate list =====
     const int qw = warp - 4;
     const int ql = qw * 32 + lane;             // query inside the tile == TMEM lane == list column
     const int q = q0 + ql;
@@ -603,7 +697,7 @@ scorer_body(const float* __restrict__ Q, const CUtensorMap& map_d, int B, int64_
       const int64_t t = tile_at(it);
       const int buf = it % SM_NACC;
       const uint32_t aph = (uint32_t)(it / SM_NACC) & 1u;
-      if ((it & 7) == 0 && q_valid && !smp) {
+      if ((screen_on || (it & 7) == 0) && q_valid && !smp) {
         tg = fmaxf(tg, tg_pending);
         tg_pending = __ldcg(tau_g + q);
       }
@@ -639,6 +733,12 @@ scorer_body(const float* __restrict__ Q, const CUtensorMap& map_d, int B, int64_
       for (int h = 0; h < HALVES; ++h)
         filter32(sc[h], t * ND_T + h * SM_ND, (it - S - seg_base) * ND_T + h * SM_ND, smp_tag);
       if (qw == 0) SM_TRACE(6, it);
+      if (screen_on) {
+        // what the screener compares against from now on
+        const float thr_now = smp ? key2f(f2key(top_s[SM_SAMPLE_TOP - 1]) + 1u)
+                                  : fmaxf(tg, strict ? key2f(f2key(tau) + 1u) : tau);
+        *(volatile float*)(thr_sh + ql) = q_valid ? thr_now : INFINITY;
+      }
       if (qw == 0) SM_TRACE(7, it);
     };
     // Publish the list: at most SM_KEEP candidates at or above the global bound go to the per-query
@@ -665,17 +765,34 @@ scorer_body(const float* __restrict__ Q, const CUtensorMap& map_d, int B, int64_
       }
       cnt = 0;
     };
-    auto main_tiles = [&]() {
-      for (; it < n_seq; ++it) {
-        if (it - S - seg_base >= seg_tiles) {   // warp-uniform
-          publish();
-          seg_base += seg_tiles;
+    auto main_tile = [&](const int it2) {
+      while (it2 - S - seg_base >= seg_tiles) {   // warp-uniform
+        publish();
+        seg_base += seg_tiles;
+      }
+      tile_body(it2, std::false_type{});
+    };
+    // screening on: process the tiles the quarter's screener queued, until it has classified tiles [0, end)
+    volatile int* hit_wr_v = hit_wr;
+    volatile int* scr_v = scr_tiles;
+    int rd = 0;
+    auto drain = [&](const int end, auto smp_tag) {
+      for (unsigned spin = 0;;) {
+        if (rd < hit_wr_v[qw]) {
+          const int it2 = *(volatile int*)&hit_q[qw][rd & 7];
+          ++rd;
+          if (decltype(smp_tag)::value) tile_body(it2, std::true_type{});
+          else main_tile(it2);
+          spin = 0;
+        } else if (scr_v[qw] >= end) {
+          if (hit_wr_v[qw] == rd) break;           // classified everything and nothing is pending
+        } else {
+          __nanosleep(32);
+          if (++spin > (1u << 27)) __trap();
         }
-        tile_body(it, std::false_type{});
       }
     };
-    if (FUSED) {
-      for (it = 0; it < S; ++it) tile_body(it, std::true_type{});
+    auto fused_barrier_phase = [&]() {
       // ---- end of the sample phase: publish, grid barrier, the CTAs select the queries' bounds, grid barrier ----
       const unsigned n_ctas = gridDim.x * gridDim.y;
       float* mine = fa.samp + ((size_t)(q0 + ql) * n_slices + slice) * SM_SAMPLE_TOP;
@@ -706,11 +823,31 @@ scorer_body(const float* __restrict__ Q, const CUtensorMap& map_d, int B, int64_
       ptx::named_bar_sync(2, SM_MQ);
       tg = q_valid ? __ldcg(tau_g + q) : INFINITY;
       tg_pending = tg;
-      main_tiles();
+      if (screen_on) {
+        *(volatile float*)(thr_sh + ql) = tg;
+        __threadfence_block();
+        __syncwarp();
+        if (lane == 0) *(volatile int*)&go_main[qw] = 1;
+      }
+    };
+    if (screen_on) {
+      if (FUSED) {
+        drain(S, std::true_type{});
+        fused_barrier_phase();
+        drain(n_seq, std::false_type{});
+      } else if (SAMPLE) {
+        drain(n_seq, std::true_type{});
+      } else {
+        drain(n_seq, std::false_type{});
+      }
+    } else if (FUSED) {
+      for (it = 0; it < S; ++it) tile_body(it, std::true_type{});
+      fused_barrier_phase();
+      for (; it < n_seq; ++it) main_tile(it);
     } else if (SAMPLE) {
       for (it = 0; it < n_seq; ++it) tile_body(it, std::true_type{});
     } else {
-      main_tiles();
+      for (it = 0; it < n_seq; ++it) main_tile(it);
     }
     if (threadIdx.x == 128) SM_MARK(2);      // last tile filtered
     if (SAMPLE) {

@@ -16,18 +16,26 @@ from typing import Optional, Sequence, Tuple, Union
 import numpy as np
 import torch
 
+from . import _lib
+
 Ragged = Tuple[np.ndarray, np.ndarray]      # (flat int64 token ids, int64 lengths)
 
 
-def plan_batches(lengths: np.ndarray, max_tokens: int, max_rows: int):
+ROW_QUANTUM = 3840     # rows of two full waves of the tcgen05 recurrence (15 co-resident 8-CTA clusters x 256 rows / 2 directions)
+
+
+def plan_batches(lengths: np.ndarray, max_tokens: int, max_rows: int, row_quantum: int = ROW_QUANTUM):
     """Greedy batches over rows sorted by length (descending): each batch holds at most
-    `max_rows` rows and `max_tokens` padded tokens.  Returns (order, [(lo, hi), ...])."""
+    `max_rows` rows and `max_tokens` padded tokens; row counts above `row_quantum` are rounded down to a
+    multiple of it so the recurrence kernel runs whole waves of clusters.  Returns (order, [(lo, hi), ...])."""
     order = np.argsort(-lengths, kind="stable")
     sl = lengths[order]
     bounds, lo, n = [], 0, len(sl)
     while lo < n:
         T = int(sl[lo])
         rows = max(1, min(max_rows, max_tokens // max(T, 1)))
+        if row_quantum > 0 and rows > row_quantum:
+            rows -= rows % row_quantum
         hi = min(n, lo + rows)
         bounds.append((lo, hi))
         lo = hi
@@ -61,7 +69,7 @@ class _Staging:
 
 
 def encode_rows(encoder, rows: Union[Ragged, Sequence[Sequence[int]]], device, out: Optional[torch.Tensor] = None,
-                out_offset: int = 0, max_tokens: int = 262144, max_rows: int = 16384) -> torch.Tensor:
+                out_offset: int = 0, max_tokens: int = 524288, max_rows: int = 15360) -> torch.Tensor:
     """Encode tokenised rows with `encoder` (an RNNEncoder) -> fp32 [n, H] on `device`
     (rows `out[out_offset : out_offset + n]` if `out` is given).  `rows` is a list of id lists or a
     (flat ids, lengths) pair.  Raises RuntimeError for empty rows like the reference's
@@ -100,13 +108,10 @@ def encode_rows(encoder, rows: Union[Ragged, Sequence[Sequence[int]]], device, o
                     st.copied.synchronize()              # the copy engine has read this buffer (two batches ago)
                 idx = order[lo:hi]
                 R, T = hi - lo, int(lengths[idx[0]])
-                # vectorised fill: padded [R, T] view of the pinned buffer <- ragged rows
-                hv = st.ids_np[:R * T].reshape(R, T)
-                ln = lengths[idx]
-                pos = np.arange(T, dtype=np.int64)[None, :]
-                mask = pos < ln[:, None]
-                hv[...] = 0
-                hv[mask] = flat[(starts[idx][:, None] + pos)[mask]]
+                # fill the padded [R, T] view of the pinned buffer from the ragged rows (host memcpy per row, in C)
+                idx = np.ascontiguousarray(idx, dtype=np.int64)
+                _lib.call_nostream("ttr_pack_padded_i64", flat.ctypes.data, starts.ctypes.data, lengths.ctypes.data,
+                                   idx.ctypes.data, R, T, st.ids.data_ptr())
                 st.idx_np[:R] = idx + out_offset
                 with torch.cuda.stream(copy_stream):
                     dev_ids = st.ids[:R * T].view(R, T).to(dev, non_blocking=True)
