@@ -182,6 +182,7 @@ int ttr_pack_padded_i64(const int64_t* flat, const int64_t* starts, const int64_
  * bit26 = CTA-pair scorer: swap which CTA loads which half of a 64-document tile (bring-up switch; breaks results),
  * bit27 = one CTA per query tile for B > 128 (the round-1 layout) instead of CTA pairs,
  * bit28 = CTA-pair scorer: cta_group::2 TMA loads counted on the leader's barrier instead of plain loads + forwarding,
+ * bit30 = fp16 projection GEMM for K > 256 on the single-CTA 128 x 128 kernel instead of CTA pairs (256 x 256 tiles),
  * bit29 = tcgen05 scorer without the screening warps (every tile goes through the list-keeping warps, as in round 1). */
 int ttr_debug_set_flags(int flags);
 int ttr_debug_get_flags(int* out);

@@ -113,3 +113,35 @@ def test_tn_weight_gradient_gemm_matches_fp64(cuda_device, M, N1, N2, lda_extra,
     assert err <= 1.5e-3 * scale, (err, scale)
     _lib.call("ttr_gemm_tn_tf32", a_view, A.shape[1], b_view, Bm.shape[1], C, N2, m_bound, mv, N1, N2, 1)
     assert float((C.double() - 2 * ref).abs().max()) <= 3e-3 * scale
+
+
+@pytest.mark.parametrize("M,N,K,mv", [(1000, 1536, 512, None), (513, 1536, 512, 300), (256, 256, 320, None), (5000, 1536, 512, 4321),
+                                      (300, 520, 264, None), (129, 104, 456, 1), (20000, 1536, 512, None)])
+def test_f16_pair_gemm_matches_fp64_and_the_single_cta_kernel(cuda_device, M, N, K, mv):
+    """K > 256 runs CTA pairs (tcgen05.mma.cta_group::2, 256 x 256 tiles, each CTA loads half of A's and half of W's rows);
+    debug bit 30 selects the single-CTA 128 x 128 kernel.  Same operands, same k order -> same fp16 results; rows at or
+    beyond the device-side row count stay untouched."""
+    g = torch.Generator(device=cuda_device).manual_seed(M + N + K)
+    A = (torch.randn(M, K, device=cuda_device, generator=g) * 0.4).half()
+    W = ((torch.rand(N, K, device=cuda_device, generator=g) - 0.5) / 8).half()
+    b = torch.randn(N, device=cuda_device, generator=g) * 0.05
+    mvt = None if mv is None else torch.tensor([mv], dtype=torch.int32, device=cuda_device)
+    out = {}
+    for name, flags in (("pair", 0), ("single", 1 << 30)):
+        C = torch.full((M, N), 7.0, dtype=torch.float16, device=cuda_device)
+        _lib.call_nostream("ttr_debug_set_flags", flags)
+        try:
+            _lib.call("ttr_gemm_f16_bias", A, W, b, C, M, mvt, N, K)
+            torch.cuda.synchronize()
+        finally:
+            _lib.call_nostream("ttr_debug_set_flags", 0)
+        out[name] = C
+    rows = M if mv is None else mv
+    ref = A[:rows].double() @ W.double().t() + b.double()
+    scale = float((A.double().abs() @ W.double().abs().t()).max())
+    err = (out["pair"][:rows].double() - ref).abs()
+    assert float((err - ref.abs() * 2.0 ** -11).max()) <= 2e-6 * max(scale, 1.0), float(err.max())
+    assert torch.equal(out["pair"][:rows], out["single"][:rows])
+    tail_lo = (rows + 255) // 256 * 256                    # rows of partially valid tiles may be written (caller-owned, never read)
+    if tail_lo < M:
+        assert (out["pair"][tail_lo:] == 7.0).all()

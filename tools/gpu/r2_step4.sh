@@ -16,3 +16,8 @@ cat gpurun_out/summary.txt; sed -n '1,3p;/^mean/,$p' gpurun_out/trace5_b256_f0.t
 timeout 300 python tools/encode_bench.py 7680 7680 > gpurun_out/plain_encode.log 2>&1
 timeout 600 ncu --set full --clock-control none --kernel-name regex:gemm_bias_kernel -c 4 -o gpurun_out/prof_r2_gemm -f python tools/encode_bench.py 7680 7680 > gpurun_out/ncu_gemm.log 2>&1
 ls -la gpurun_out/prof_r2_gemm.ncu-rep
+for f in test_gpu_gemm test_gpu_towers; do
+  timeout 600 python -m pytest tests/$f.py -q -m gpu -x --timeout=300 > gpurun_out/$f.log 2>&1
+  echo "$f exit $? $(tail -1 gpurun_out/$f.log)" | tee -a gpurun_out/summary.txt
+done
+timeout 300 python tools/encode_bench.py 7680 7680 > gpurun_out/plain_encode_pair.log 2>&1; tail -12 gpurun_out/plain_encode_pair.log

@@ -136,6 +136,8 @@ gemm_bias_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         if (ptx::elect_one()) {
 #pragma unroll
           for (int k = 0; k < GK / 8; ++k) {
+            // k-steps that start at or beyond K multiply TMA zero fill only (K = 200: 13 of 16 fp16 steps are real)
+            if ((kb * (GK / 8) + k) * (F16 ? 16 : 8) >= K) continue;
             // advance 8 tf32 / 16 halves = 32 bytes inside the 128-byte swizzle row: +2 in 16-byte units
             if (F16) ptx::mma_f16_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
             else ptx::mma_tf32_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
@@ -277,6 +279,191 @@ gemm_bias_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   if (warp == 2) ptx::tmem_dealloc(tmem_base, G_TMEM_COLS);
 }
 
+// ---- CTA-pair variant (fp16, K > 256): 256 x 256 output tiles on tcgen05.mma.cta_group::2 -----------------------
+// The single-CTA kernel above streams a 128-row A block AND a 128-row W block per 128 x 128 x 64 step; at K = 512
+// (no room for a resident W tile) that is 32 KB of operands per 2 MFLOP and the L2 -> SM fabric, not the tensor pipe,
+// sets the rate (r1 ncu: 11.9 TB/s delivered to the SMs, tensor pipe 39 % active).  Here the two CTAs of a cluster
+// compute ONE 256 x 256 tile: CTA r loads rows [m0 + 128 r, +128) of A and rows [n0 + 128 r, +128) of W — the same
+// 32 KB per stage — and the pair's M = 256, N = 256 MMA reads both W halves, so each SM does twice the MMA work per
+// operand byte it fetches.  Each CTA's tensor memory holds its 128 x 256 block of the tile (two buffers = all 512
+// columns); its two epilogue groups write it out exactly like the single-CTA kernel, 128 columns at a time.
+// Synchronisation as in the CTA-pair scorer (score_topk_mma.cu): plain TMA loads onto the CTA's own `full` barrier,
+// the peer's warp 1 forwards each completion to the leader's `peer_full`, tcgen05.commit multicasts `stage free` and
+// `accumulator full`, the peer's epilogue warps release accumulators with remote arrives on the leader's barrier.
+constexpr int GP_ACC_COLS = 256;
+constexpr int GP_TMEM_COLS = 512;
+
+__global__ void __launch_bounds__(G_THREADS, 1)
+gemm_bias_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
+                      const float* __restrict__ bias, int m_bound, const int32_t* __restrict__ m_valid, int N, int K,
+                      int dbg, __half* __restrict__ c_out, int n_stages) {
+  extern __shared__ unsigned char smem_raw[];
+  constexpr int GKE = 2 * GK;                       // halves per 128-byte k-block
+  unsigned char* tiles = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
+  unsigned char* out_stage = tiles + n_stages * G_STAGE_BYTES;      // per epilogue group
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(out_stage + 2 * G_F16_STAGE);
+  uint64_t* empty_bar = full_bar + G_MAX_STAGES;
+  uint64_t* peer_full = empty_bar + G_MAX_STAGES;   // leader only: the peer's half of stage s has landed
+  uint64_t* acc_full = peer_full + G_MAX_STAGES;    // [2] MMA -> epilogue
+  uint64_t* acc_empty = acc_full + 2;               // [2] epilogue -> MMA (leader's: both CTAs' groups arrive)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = ptx::cluster_ctarank();
+  const bool leader = rank == 0u;
+  const int M = m_valid ? min(m_bound, *m_valid) : m_bound;
+  const int m_tiles = ceil_div(M, 2 * GM), n_tiles = ceil_div(N, 2 * GN);
+  const int total_tiles = m_tiles * n_tiles;
+  const int k_blocks = ceil_div(K, GKE);
+  const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < n_stages; ++s) {
+      ptx::mbar_init(full_bar + s, 1); ptx::mbar_init(empty_bar + s, 1); ptx::mbar_init(peer_full + s, 1);
+    }
+    for (int b = 0; b < 2; ++b) { ptx::mbar_init(acc_full + b, 1); ptx::mbar_init(acc_empty + b, 8); }
+    ptx::fence_mbar_init();
+  }
+  if (warp == 2) {
+    ptx::tmem_alloc_2cta(tmem_slot, GP_TMEM_COLS);
+    ptx::tmem_relinquish_2cta();
+  }
+  ptx::tc_fence_before_sync();
+  ptx::cluster_sync();                    // both CTAs' barriers exist before any multicast commit / remote arrive
+  ptx::tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer: this CTA's 128 rows of A and 128 rows of W per k-block =====
+    if (ptx::elect_one()) {
+      ptx::prefetch_tensormap(&map_a);
+      ptx::prefetch_tensormap(&map_w);
+    }
+    int it = 0;
+    for (int tile = pair; tile < total_tiles; tile += n_pairs) {
+      const int m0 = (tile / n_tiles) * 2 * GM + (int)rank * GM, n0 = (tile % n_tiles) * 2 * GN + (int)rank * GN;
+      for (int kb = 0; kb < k_blocks; ++kb, ++it) {
+        const int s = it % n_stages;
+        const uint32_t ph = (uint32_t)(it / n_stages) & 1u;
+        ptx::mbar_wait(empty_bar + s, ph ^ 1u);
+        unsigned char* a_dst = tiles + s * G_STAGE_BYTES;
+        if (ptx::elect_one()) {
+          ptx::mbar_arrive_expect_tx(full_bar + s, G_STAGE_BYTES);
+          ptx::tma_load_2d(a_dst, &map_a, kb * GKE, m0, full_bar + s);
+          ptx::tma_load_2d(a_dst + G_A_BYTES, &map_w, kb * GKE, n0, full_bar + s);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == 1 && leader) {
+    // ===== MMA issuer (leader CTA): M = 256 (128 rows per CTA), N = 256 (128 W rows per CTA), K = 16 =====
+    constexpr uint32_t idesc = ptx::make_idesc_f16(2 * GM, 2 * GN);
+    int it = 0, local = 0;
+    for (int tile = pair; tile < total_tiles; tile += n_pairs, ++local) {
+      const int buf = local & 1;
+      const uint32_t aph = (uint32_t)(local >> 1) & 1u;
+      ptx::mbar_wait(acc_empty + buf, aph ^ 1u);       // both CTAs' epilogues drained this accumulator
+      ptx::tc_fence_after_sync();
+      const uint32_t d_tmem = tmem_base + buf * GP_ACC_COLS;
+      for (int kb = 0; kb < k_blocks; ++kb, ++it) {
+        const int s = it % n_stages;
+        const uint32_t ph = (uint32_t)(it / n_stages) & 1u;
+        ptx::mbar_wait(full_bar + s, ph);
+        ptx::mbar_wait(peer_full + s, ph);
+        ptx::tc_fence_after_sync();
+        const uint32_t a_addr = ptx::smem_u32(tiles + s * G_STAGE_BYTES);
+        const uint64_t a_desc = ptx::make_kmajor_sw128_desc(a_addr);
+        const uint64_t b_desc = ptx::make_kmajor_sw128_desc(a_addr + G_A_BYTES);
+        if (ptx::elect_one()) {
+#pragma unroll
+          for (int k = 0; k < GK / 8; ++k)
+            if ((kb * (GK / 8) + k) * 16 < K)          // k-steps beyond K hold only zero fill (K = 200: 13 of 16)
+              ptx::mma_f16_ss_2cta(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+          ptx::mma_commit_2cta(empty_bar + s, 3);                      // both CTAs' stage s is free
+          if (kb == k_blocks - 1) ptx::mma_commit_2cta(acc_full + buf, 3);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == 1) {
+    // ===== peer CTA: forward "my half of stage s has landed" to the leader's MMA issuer =====
+    int it = 0;
+    for (int tile = pair; tile < total_tiles; tile += n_pairs)
+      for (int kb = 0; kb < k_blocks; ++kb, ++it) {
+        const int s = it % n_stages;
+        ptx::mbar_wait(full_bar + s, (uint32_t)(it / n_stages) & 1u);
+        if (ptx::elect_one()) ptx::mbar_arrive_cluster(ptx::mapa(ptx::smem_u32(peer_full + s), 0u));
+        __syncwarp();
+      }
+  } else if (warp >= 4) {
+    // ===== epilogue: this CTA's 128 x 256 block, 128 columns at a time through the row-major fp16 staging =====
+    const int grp = (warp - 4) >> 2;
+    const int q = (warp - 4) & 3;                         // TMEM lane quadrant of this warp
+    const int r_in_tile = q * 32 + lane;
+    unsigned char* my_stage = out_stage + grp * G_F16_STAGE;
+    int local = 0;
+    for (int tile = pair; tile < total_tiles; tile += n_pairs, ++local) {
+      const int buf = local & 1;
+      if (buf != grp) continue;
+      const uint32_t aph = (uint32_t)(local >> 1) & 1u;
+      const int m0 = (tile / n_tiles) * 2 * GM + (int)rank * GM, nt0 = (tile % n_tiles) * 2 * GN;
+      ptx::mbar_wait(acc_full + buf, aph);
+      ptx::tc_fence_after_sync();
+#pragma unroll 1
+      for (int ch = 0; ch < 2; ++ch) {
+        const int n0 = nt0 + ch * GN;
+#pragma unroll 1
+        for (int c0 = 0; c0 < GN; c0 += 32) {
+          uint32_t r[32];
+          ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * GP_ACC_COLS + ch * GN + c0, r);
+          ptx::tmem_ld_wait();
+          if (ch == 1 && c0 + 32 >= GN) {                 // last read of this accumulator: hand it back
+            ptx::tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) {
+              if (leader) ptx::mbar_arrive(acc_empty + buf);
+              else ptx::mbar_arrive_cluster(ptx::mapa(ptx::smem_u32(acc_empty + buf), 0u));
+            }
+          }
+          uint4* row = reinterpret_cast<uint4*>(my_stage + r_in_tile * G_F16_PITCH + c0 * 2);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {                   // four 16-byte chunks = 32 halves
+            const int n = n0 + c0 + 8 * j;
+            float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
+            if (bias && n + 7 < N) {
+              b0 = __ldg(reinterpret_cast<const float4*>(bias + n));
+              b1 = __ldg(reinterpret_cast<const float4*>(bias + n + 4));
+            }
+            const __half2 h0 = __floats2half2_rn(__uint_as_float(r[8 * j + 0]) + b0.x, __uint_as_float(r[8 * j + 1]) + b0.y);
+            const __half2 h1 = __floats2half2_rn(__uint_as_float(r[8 * j + 2]) + b0.z, __uint_as_float(r[8 * j + 3]) + b0.w);
+            const __half2 h2 = __floats2half2_rn(__uint_as_float(r[8 * j + 4]) + b1.x, __uint_as_float(r[8 * j + 5]) + b1.y);
+            const __half2 h3 = __floats2half2_rn(__uint_as_float(r[8 * j + 6]) + b1.z, __uint_as_float(r[8 * j + 7]) + b1.w);
+            row[j] = make_uint4(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1),
+                                *reinterpret_cast<const uint32_t*>(&h2), *reinterpret_cast<const uint32_t*>(&h3));
+          }
+        }
+        ptx::named_bar_sync(1 + grp, 128);
+        if (!(dbg & 2048)) {
+          const int half_lane = lane & 15, sub = lane >> 4;
+          const int ncol = n0 + 8 * half_lane;
+#pragma unroll 4
+          for (int rr = q * 32; rr < q * 32 + 32; rr += 2) {          // this warp's 32 rows, two per instruction
+            const int rrow = rr + sub;
+            const uint4 v = *reinterpret_cast<const uint4*>(my_stage + rrow * G_F16_PITCH + 16 * half_lane);
+            if (m0 + rrow < M && ncol + 7 < N)
+              *reinterpret_cast<uint4*>(c_out + (size_t)(m0 + rrow) * N + ncol) = v;
+          }
+        }
+        ptx::named_bar_sync(1 + grp, 128);                // staging is free again
+      }
+    }
+  }
+
+  ptx::tc_fence_before_sync();
+  ptx::cluster_sync();                    // the peer's MMAs / commits / remote arrives no longer target this CTA
+  if (warp == 2) ptx::tmem_dealloc_2cta(tmem_base, GP_TMEM_COLS);
+}
+
 // ---- host: tensor maps ------------------------------------------------------------------
 static PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
   static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
@@ -373,6 +560,36 @@ extern "C" int ttr_gemm_f16_bias(const void* A16, const void* W16, const float* 
     gemm_bias_kernel<true, true><<<n_tiles * per_n, G_THREADS, smem_res, (cudaStream_t)stream>>>(
         map_a, map_w, map_c, bias, m_bound, m_valid, N, K, g_debug_flags, C16, ws_stages, 2);
     TTR_CHECK_LAUNCH();
+    return TTR_OK;
+  }
+  if (!(g_debug_flags & (1 << 30)) && sm_count() >= 2) {
+    // CTA pairs, 256 x 256 tiles (debug bit 30: the single-CTA 128 x 128 kernel below, for A/B)
+    constexpr int STP = 4;
+    const size_t smem_p = (size_t)STP * G_STAGE_BYTES + 2 * (size_t)G_F16_STAGE + (3 * G_MAX_STAGES + 4) * sizeof(uint64_t) + 16 + 1024;
+    static thread_local int attr_dev = -1;
+    int cur_dev = 0;
+    TTR_CHECK_CUDA(cudaGetDevice(&cur_dev));
+    if (attr_dev != cur_dev) {
+      TTR_CHECK_CUDA(cudaFuncSetAttribute(gemm_bias_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_p));
+      attr_dev = cur_dev;
+    }
+    const int pair_tiles = ceil_div(m_bound, 2 * GM) * ceil_div(N, 2 * GN);
+    const int pairs = std::max(1, std::min(pair_tiles, sm_count() / 2));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * pairs);
+    cfg.blockDim = dim3(G_THREADS);
+    cfg.dynamicSmemBytes = smem_p;
+    cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    int dbgv = g_debug_flags, stp = STP;
+    __half* c16 = reinterpret_cast<__half*>(C16);
+    void* args[] = {(void*)&map_a, (void*)&map_w, (void*)&bias, (void*)&m_bound, (void*)&m_valid, (void*)&N, (void*)&K,
+                    (void*)&dbgv, (void*)&c16, (void*)&stp};
+    TTR_CHECK_CUDA(cudaLaunchKernelExC(&cfg, (const void*)gemm_bias_pair_kernel, args));
     return TTR_OK;
   }
   constexpr int ST16 = 4;                  // 4 x 32 KB ring + two 34 KB staging groups (1.80 ms per 1.0 M tokens at

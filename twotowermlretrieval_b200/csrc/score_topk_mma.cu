@@ -533,8 +533,30 @@ scorer_body(const float* __restrict__ Q, const CUtensorMap& map_d, int B, int64_
     float tgp = (q_valid && MODE == 0) ? __ldcg(tau_g + q) : (q_valid ? -INFINITY : INFINITY);
     float tgp_pending = tgp;
     int wr = 0;
+    // Sample phase: the screener alone serves it.  Per tile it keeps the thread's MAXIMUM (the FMNMX tree it computes
+    // anyway) and the best SM_SAMPLE_TOP tile maxima of the phase; those are published instead of an exact per-thread
+    // top-4.  Every published value is the score of a distinct real document, so the k-th best of the union over all
+    // CTAs is still a valid lower bound on the final k-th best (a tile holding two of the sample's top k contributes
+    // one: the bound is marginally looser).  The exact top-4 insertion it replaces ran a 32-iteration warp-uniform
+    // loop per tile while the thresholds were loose: 5-17 k cycles per tile, 40-70 us per search on small shards.
+    float smp_s[SM_SAMPLE_TOP];
+    int32_t smp_i[SM_SAMPLE_TOP];
+#pragma unroll
+    for (int e = 0; e < SM_SAMPLE_TOP; ++e) { smp_s[e] = -INFINITY; smp_i[e] = -1; }
+    auto publish_sample_fused = [&]() {
+      float* mine = fa.samp + ((size_t)(q0 + ql) * n_slices + slice) * SM_SAMPLE_TOP;
+#pragma unroll
+      for (int e = 0; e < SM_SAMPLE_TOP; ++e) mine[e] = (q_valid && smp_i[e] >= 0) ? smp_s[e] : -INFINITY;
+      __threadfence();
+    };
     for (int it = 0; screen_on && it < n_seq; ++it) {
       if (FUSED && it == S) {
+        publish_sample_fused();
+        __syncwarp();
+        if (lane == 0) {
+          __threadfence_block();
+          scr_v[qw] = S;                       // the keeper may start the grid-barrier phase
+        }
         // the keeper publishes the seeded bounds after the grid barriers; main tiles must not be judged by the
         // sample thresholds (those say "beats my 4th best", not "can be in the top k")
         for (unsigned spin = 0; go_v[qw] == 0; ++spin) {
@@ -572,9 +594,24 @@ scorer_body(const float* __restrict__ Q, const CUtensorMap& map_d, int B, int64_
           mx = fmaxf(mx, m16[0]);
         }
       }
-      const float thr = fmaxf(thr_v[ql], smp ? -INFINITY : tgp);
-      // the last tile holds zero-filled rows beyond N: the keeper masks them, so it always gets that tile
-      const bool hit = __any_sync(0xffffffffu, mx >= thr) || (t + 1) * ND_T > N;
+      const bool tail = (t + 1) * ND_T > N;    // zero-filled rows beyond N (score 0 is not a document's score)
+      if (smp) {
+        float cs = (q_valid && !tail) ? mx : -INFINITY;
+        int32_t ci = (int32_t)(t * ND_T);      // a distinct id per tile (the merge of the sample pass wants distinct keys)
+#pragma unroll
+        for (int e = 0; e < SM_SAMPLE_TOP; ++e) {
+          const bool up = cs > smp_s[e];
+          const float ts = smp_s[e];
+          const int32_t ti = smp_i[e];
+          smp_s[e] = up ? cs : ts;
+          smp_i[e] = up ? ci : ti;
+          cs = up ? ts : cs;
+          ci = up ? ti : ci;
+        }
+      }
+      const float thr = fmaxf(thr_v[ql], tgp);
+      // the keeper masks the zero-filled rows of the last tile, so it always gets that tile
+      const bool hit = !smp && (__any_sync(0xffffffffu, mx >= thr) || tail);
       if (!hit) {
         ptx::tc_fence_before_sync();
         __syncwarp();
@@ -590,10 +627,19 @@ scorer_body(const float* __restrict__ Q, const CUtensorMap& map_d, int B, int64_
         }
         ++wr;
       }
-      if (lane == 0) {
+      if (lane == 0 && !(FUSED && it + 1 == S)) {      // "sample done" is signalled after the sample values are written
         __threadfence_block();
         scr_v[qw] = it + 1;
       }
+    }
+    if (screen_on && SAMPLE && q_valid) {            // separate sample pass: tile maxima -> candidate scratch
+      int n_keep = 0;
+#pragma unroll
+      for (int e = 0; e < SM_SAMPLE_TOP; ++e) n_keep += smp_i[e] >= 0 ? 1 : 0;
+      size_t ob = (size_t)q * (size_t)cap + (size_t)atomicAdd(out_n + q, n_keep);
+#pragma unroll
+      for (int e = 0; e < SM_SAMPLE_TOP; ++e)
+        if (smp_i[e] >= 0) { out_s[ob] = smp_s[e]; out_i[ob] = smp_i[e]; ++ob; }
     }
   } else if (warp >= 4) {
     // ===== keeper: one thread per query; owns the candidate list =====
@@ -795,9 +841,11 @@ scorer_body(const float* __restrict__ Q, const CUtensorMap& map_d, int B, int64_
     auto fused_barrier_phase = [&]() {
       // ---- end of the sample phase: publish, grid barrier, the CTAs select the queries' bounds, grid barrier ----
       const unsigned n_ctas = gridDim.x * gridDim.y;
-      float* mine = fa.samp + ((size_t)(q0 + ql) * n_slices + slice) * SM_SAMPLE_TOP;
+      if (!screen_on) {                        // (with screening the screener has published its tile maxima)
+        float* mine = fa.samp + ((size_t)(q0 + ql) * n_slices + slice) * SM_SAMPLE_TOP;
 #pragma unroll
-      for (int e = 0; e < SM_SAMPLE_TOP; ++e) mine[e] = (q_valid && top_i[e] >= 0) ? top_s[e] : -INFINITY;
+        for (int e = 0; e < SM_SAMPLE_TOP; ++e) mine[e] = (q_valid && top_i[e] >= 0) ? top_s[e] : -INFINITY;
+      }
       __threadfence();
       ptx::named_bar_sync(2, SM_MQ);
       if (ql == 0) {
@@ -851,7 +899,7 @@ scorer_body(const float* __restrict__ Q, const CUtensorMap& map_d, int B, int64_
     }
     if (threadIdx.x == 128) SM_MARK(2);      // last tile filtered
     if (SAMPLE) {
-      if (q_valid) {
+      if (q_valid && !screen_on) {
         int n_keep = 0;
 #pragma unroll
         for (int e = 0; e < SM_SAMPLE_TOP; ++e) n_keep += top_i[e] >= 0 ? 1 : 0;
