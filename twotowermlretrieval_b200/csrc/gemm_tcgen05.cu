@@ -32,6 +32,40 @@ __host__ __device__ constexpr int stage_area(bool f16) { return f16 ? G_F16_STAG
 
 extern int g_debug_flags;
 
+// fp16 epilogue of one 128-row x 128-column block: TMEM -> registers (+bias from shared memory) -> row-major fp16
+// staging.  The four tcgen05.ld of the block are double-buffered (chunk c + 1 is in flight while chunk c is converted)
+// and the bias comes from a 512-byte shared copy of the tile's bias slice: r2 ncu of the K = 200 layer showed the
+// epilogue groups, not loads / MMAs / DRAM, setting the tile rate (tensor pipe 28 %, DRAM 44 %, top stall
+// long_scoreboard = the eight `__ldg(bias)` per 32-column chunk in front of every conversion).
+// `release` is called right after the last tcgen05.ld of the block has completed.
+template <typename Release>
+__device__ __forceinline__ void f16_block_to_stage(uint32_t tmem_col0, int q, int r_in_tile, unsigned char* my_stage,
+                                                   const float* __restrict__ bias_sm, bool last_block, Release release) {
+  uint32_t ra[32], rb[32];
+  const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+  ptx::tmem_ld_32x32(tmem_col0 + lane_base, ra);
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    uint32_t (&cur)[32] = (c & 1) ? rb : ra;
+    uint32_t (&nxt)[32] = (c & 1) ? ra : rb;
+    ptx::tmem_ld_wait();
+    if (c < 3) ptx::tmem_ld_32x32(tmem_col0 + lane_base + 32 * (c + 1), nxt);
+    else if (last_block) release();
+    uint4* row = reinterpret_cast<uint4*>(my_stage + r_in_tile * G_F16_PITCH + c * 64);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {                   // four 16-byte chunks = 32 halves
+      const float4 b0 = *reinterpret_cast<const float4*>(bias_sm + 32 * c + 8 * j);
+      const float4 b1 = *reinterpret_cast<const float4*>(bias_sm + 32 * c + 8 * j + 4);
+      const __half2 h0 = __floats2half2_rn(__uint_as_float(cur[8 * j + 0]) + b0.x, __uint_as_float(cur[8 * j + 1]) + b0.y);
+      const __half2 h1 = __floats2half2_rn(__uint_as_float(cur[8 * j + 2]) + b0.z, __uint_as_float(cur[8 * j + 3]) + b0.w);
+      const __half2 h2 = __floats2half2_rn(__uint_as_float(cur[8 * j + 4]) + b1.x, __uint_as_float(cur[8 * j + 5]) + b1.y);
+      const __half2 h3 = __floats2half2_rn(__uint_as_float(cur[8 * j + 6]) + b1.z, __uint_as_float(cur[8 * j + 7]) + b1.w);
+      row[j] = make_uint4(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1),
+                          *reinterpret_cast<const uint32_t*>(&h2), *reinterpret_cast<const uint32_t*>(&h3));
+    }
+  }
+}
+
 // F16 = true: A, W and C are fp16 (kind::f16 MMAs, 64 halves per 128-byte k-block, fp32 accumulation and
 // bias add, fp16 result) — the encode path's variant.  fp16 and tf32 carry the same 11-bit significand, so
 // the products are as exact as the tf32 ones; what changes is the traffic: operands and the 6 KB/token gi
@@ -161,6 +195,9 @@ gemm_bias_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     const int q = (warp - 4) & 3;                         // TMEM lane quadrant of this warp
     const int r_in_tile = q * 32 + lane;
     unsigned char* my_stage = out_stage + grp * stage_area(F16);
+    __shared__ float bias_tiles[2][GN];                   // per epilogue group: bias slice of the current column tile
+    float* bias_sm = bias_tiles[grp];
+    int bias_n0 = -1;
     int local = 0, chunk_no = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
       const int buf = local & 1;
@@ -174,33 +211,18 @@ gemm_bias_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         // plain coalesced stores, two full 256-byte row segments per warp instruction.  (TMA stores of
         // 128-byte-wide boxes — the SWIZZLE_128B limit — issue one 128 B segment per row and measured
         // 2.1 TB/s on this layout; per-thread row stores 1.1 TB/s.)
-#pragma unroll 1
-        for (int c0 = 0; c0 < GN; c0 += 32) {
-          uint32_t r[32];
-          ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * G_ACC_COLS + c0, r);
-          ptx::tmem_ld_wait();
-          if (c0 + 32 >= GN) {                            // last read of this accumulator: hand it back
-            ptx::tc_fence_before_sync();
-            __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(acc_empty + buf);
-          }
-          uint4* row = reinterpret_cast<uint4*>(my_stage + r_in_tile * G_F16_PITCH + c0 * 2);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {                   // four 16-byte chunks = 32 halves
-            const int n = n0 + c0 + 8 * j;
-            float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
-            if (bias && n + 7 < N) {
-              b0 = __ldg(reinterpret_cast<const float4*>(bias + n));
-              b1 = __ldg(reinterpret_cast<const float4*>(bias + n + 4));
-            }
-            const __half2 h0 = __floats2half2_rn(__uint_as_float(r[8 * j + 0]) + b0.x, __uint_as_float(r[8 * j + 1]) + b0.y);
-            const __half2 h1 = __floats2half2_rn(__uint_as_float(r[8 * j + 2]) + b0.z, __uint_as_float(r[8 * j + 3]) + b0.w);
-            const __half2 h2 = __floats2half2_rn(__uint_as_float(r[8 * j + 4]) + b1.x, __uint_as_float(r[8 * j + 5]) + b1.y);
-            const __half2 h3 = __floats2half2_rn(__uint_as_float(r[8 * j + 6]) + b1.z, __uint_as_float(r[8 * j + 7]) + b1.w);
-            row[j] = make_uint4(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1),
-                                *reinterpret_cast<const uint32_t*>(&h2), *reinterpret_cast<const uint32_t*>(&h3));
-          }
+        if (n0 != bias_n0) {                              // (weight-stationary: once per CTA)
+          ptx::named_bar_sync(1 + grp, 128);              // nobody still reads the previous slice
+          const int n = n0 + r_in_tile;
+          bias_sm[r_in_tile] = (bias && n < N) ? __ldg(bias + n) : 0.f;
+          bias_n0 = n0;
+          ptx::named_bar_sync(1 + grp, 128);
         }
+        f16_block_to_stage(tmem_base + buf * G_ACC_COLS, q, r_in_tile, my_stage, bias_sm, true, [&]() {
+          ptx::tc_fence_before_sync();                    // last read of this accumulator: hand it back
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(acc_empty + buf);
+        });
         ptx::named_bar_sync(1 + grp, 128);
         if (!(dbg & 2048)) {
           __half* cbase = reinterpret_cast<__half*>(c_out);
@@ -292,6 +314,43 @@ gemm_bias_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 // `accumulator full`, the peer's epilogue warps release accumulators with remote arrives on the leader's barrier.
 constexpr int GP_ACC_COLS = 256;
 constexpr int GP_TMEM_COLS = 512;
+// The ring sets this kernel's speed: a stage is reloaded only after its MMAs retire, and a load takes ~3.5 k cycles
+// under load, so stages / (3.5 k + 512) k-blocks complete per cycle (r2: 7,960 cycles per K = 512 tile with 4 stages,
+// exactly that model).  The epilogue staging is therefore only 64 columns wide (18 KB per group instead of 34 KB):
+// that buys a fifth 32 KB stage.
+constexpr int GP_HALF = 64;                               // columns staged at a time
+constexpr int GP_PITCH = GP_HALF * 2 + 16;                // staging row: 128 B + 16 B pad (conflict-free)
+constexpr int GP_STAGE = GM * GP_PITCH;                   // 18 KB per epilogue group
+constexpr int GP_STAGES = 5;
+
+// fp16 epilogue of 128 rows x 64 columns: two double-buffered tcgen05.ld of 32 columns, bias from shared memory,
+// row-major fp16 staging (GP_PITCH).  `release` runs after the last tcgen05.ld when `last` is set.
+template <typename Release>
+__device__ __forceinline__ void f16_half_to_stage(uint32_t tmem_col0, int q, int r_in_tile, unsigned char* my_stage,
+                                                  const float* __restrict__ bias_sm, bool last, Release release) {
+  uint32_t ra[32], rb[32];
+  const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+  ptx::tmem_ld_32x32(tmem_col0 + lane_base, ra);
+  ptx::tmem_ld_32x32(tmem_col0 + lane_base + 32, rb);
+  ptx::tmem_ld_wait();
+  if (last) release();
+#pragma unroll
+  for (int c = 0; c < 2; ++c) {
+    uint32_t (&cur)[32] = c ? rb : ra;
+    uint4* row = reinterpret_cast<uint4*>(my_stage + r_in_tile * GP_PITCH + c * 64);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {                   // four 16-byte chunks = 32 halves
+      const float4 b0 = *reinterpret_cast<const float4*>(bias_sm + 32 * c + 8 * j);
+      const float4 b1 = *reinterpret_cast<const float4*>(bias_sm + 32 * c + 8 * j + 4);
+      const __half2 h0 = __floats2half2_rn(__uint_as_float(cur[8 * j + 0]) + b0.x, __uint_as_float(cur[8 * j + 1]) + b0.y);
+      const __half2 h1 = __floats2half2_rn(__uint_as_float(cur[8 * j + 2]) + b0.z, __uint_as_float(cur[8 * j + 3]) + b0.w);
+      const __half2 h2 = __floats2half2_rn(__uint_as_float(cur[8 * j + 4]) + b1.x, __uint_as_float(cur[8 * j + 5]) + b1.y);
+      const __half2 h3 = __floats2half2_rn(__uint_as_float(cur[8 * j + 6]) + b1.z, __uint_as_float(cur[8 * j + 7]) + b1.w);
+      row[j] = make_uint4(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1),
+                          *reinterpret_cast<const uint32_t*>(&h2), *reinterpret_cast<const uint32_t*>(&h3));
+    }
+  }
+}
 
 __global__ void __launch_bounds__(G_THREADS, 1)
 gemm_bias_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
@@ -301,7 +360,7 @@ gemm_bias_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
   constexpr int GKE = 2 * GK;                       // halves per 128-byte k-block
   unsigned char* tiles = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
   unsigned char* out_stage = tiles + n_stages * G_STAGE_BYTES;      // per epilogue group
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(out_stage + 2 * G_F16_STAGE);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(out_stage + 2 * GP_STAGE);
   uint64_t* empty_bar = full_bar + G_MAX_STAGES;
   uint64_t* peer_full = empty_bar + G_MAX_STAGES;   // leader only: the peer's half of stage s has landed
   uint64_t* acc_full = peer_full + G_MAX_STAGES;    // [2] MMA -> epilogue
@@ -400,56 +459,49 @@ gemm_bias_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
     const int grp = (warp - 4) >> 2;
     const int q = (warp - 4) & 3;                         // TMEM lane quadrant of this warp
     const int r_in_tile = q * 32 + lane;
-    unsigned char* my_stage = out_stage + grp * G_F16_STAGE;
+    unsigned char* my_stage = out_stage + grp * GP_STAGE;
+    __shared__ float bias_tiles[2][2 * GN];               // per epilogue group: bias slice of the current 256-column tile
+    float* bias_sm = bias_tiles[grp];
+    int bias_n0 = -1;
     int local = 0;
     for (int tile = pair; tile < total_tiles; tile += n_pairs, ++local) {
       const int buf = local & 1;
       if (buf != grp) continue;
       const uint32_t aph = (uint32_t)(local >> 1) & 1u;
       const int m0 = (tile / n_tiles) * 2 * GM + (int)rank * GM, nt0 = (tile % n_tiles) * 2 * GN;
+      if (nt0 != bias_n0) {
+        ptx::named_bar_sync(1 + grp, 128);                // nobody still reads the previous slice
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int n = nt0 + h * GN + r_in_tile;
+          bias_sm[h * GN + r_in_tile] = (bias && n < N) ? __ldg(bias + n) : 0.f;
+        }
+        bias_n0 = nt0;
+        ptx::named_bar_sync(1 + grp, 128);
+      }
       ptx::mbar_wait(acc_full + buf, aph);
       ptx::tc_fence_after_sync();
 #pragma unroll 1
-      for (int ch = 0; ch < 2; ++ch) {
-        const int n0 = nt0 + ch * GN;
-#pragma unroll 1
-        for (int c0 = 0; c0 < GN; c0 += 32) {
-          uint32_t r[32];
-          ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * GP_ACC_COLS + ch * GN + c0, r);
-          ptx::tmem_ld_wait();
-          if (ch == 1 && c0 + 32 >= GN) {                 // last read of this accumulator: hand it back
-            ptx::tc_fence_before_sync();
-            __syncwarp();
-            if (lane == 0) {
-              if (leader) ptx::mbar_arrive(acc_empty + buf);
-              else ptx::mbar_arrive_cluster(ptx::mapa(ptx::smem_u32(acc_empty + buf), 0u));
-            }
+      for (int ch = 0; ch < 2 * GN / GP_HALF; ++ch) {       // four 64-column pieces of the 256-column block
+        const int n0 = nt0 + ch * GP_HALF;
+        f16_half_to_stage(tmem_base + buf * GP_ACC_COLS + ch * GP_HALF, q, r_in_tile, my_stage, bias_sm + ch * GP_HALF,
+                          ch == 2 * GN / GP_HALF - 1, [&]() {
+          ptx::tc_fence_before_sync();                    // last read of this accumulator: hand it back
+          __syncwarp();
+          if (lane == 0) {
+            if (leader) ptx::mbar_arrive(acc_empty + buf);
+            else ptx::mbar_arrive_cluster(ptx::mapa(ptx::smem_u32(acc_empty + buf), 0u));
           }
-          uint4* row = reinterpret_cast<uint4*>(my_stage + r_in_tile * G_F16_PITCH + c0 * 2);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {                   // four 16-byte chunks = 32 halves
-            const int n = n0 + c0 + 8 * j;
-            float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
-            if (bias && n + 7 < N) {
-              b0 = __ldg(reinterpret_cast<const float4*>(bias + n));
-              b1 = __ldg(reinterpret_cast<const float4*>(bias + n + 4));
-            }
-            const __half2 h0 = __floats2half2_rn(__uint_as_float(r[8 * j + 0]) + b0.x, __uint_as_float(r[8 * j + 1]) + b0.y);
-            const __half2 h1 = __floats2half2_rn(__uint_as_float(r[8 * j + 2]) + b0.z, __uint_as_float(r[8 * j + 3]) + b0.w);
-            const __half2 h2 = __floats2half2_rn(__uint_as_float(r[8 * j + 4]) + b1.x, __uint_as_float(r[8 * j + 5]) + b1.y);
-            const __half2 h3 = __floats2half2_rn(__uint_as_float(r[8 * j + 6]) + b1.z, __uint_as_float(r[8 * j + 7]) + b1.w);
-            row[j] = make_uint4(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1),
-                                *reinterpret_cast<const uint32_t*>(&h2), *reinterpret_cast<const uint32_t*>(&h3));
-          }
-        }
+        });
         ptx::named_bar_sync(1 + grp, 128);
         if (!(dbg & 2048)) {
-          const int half_lane = lane & 15, sub = lane >> 4;
-          const int ncol = n0 + 8 * half_lane;
+          // 128-byte row segments: eight lanes per row, four rows per warp instruction
+          const int chunk = lane & 7, sub = lane >> 3;
+          const int ncol = n0 + 8 * chunk;
 #pragma unroll 4
-          for (int rr = q * 32; rr < q * 32 + 32; rr += 2) {          // this warp's 32 rows, two per instruction
+          for (int rr = q * 32; rr < q * 32 + 32; rr += 4) {
             const int rrow = rr + sub;
-            const uint4 v = *reinterpret_cast<const uint4*>(my_stage + rrow * G_F16_PITCH + 16 * half_lane);
+            const uint4 v = *reinterpret_cast<const uint4*>(my_stage + rrow * GP_PITCH + 16 * chunk);
             if (m0 + rrow < M && ncol + 7 < N)
               *reinterpret_cast<uint4*>(c_out + (size_t)(m0 + rrow) * N + ncol) = v;
           }
@@ -547,25 +599,11 @@ extern "C" int ttr_gemm_f16_bias(const void* A16, const void* W16, const float* 
   const int tiles = m_tiles * n_tiles;
   const int k_blocks = ceil_div(K, 2 * GK);
   const size_t misc = (2 * G_MAX_STAGES + 5) * sizeof(uint64_t) + 16 + 1024;
-  // weight-stationary when the W tile fits next to a >= 5-deep A ring and two epilogue groups (K <= 256) and every
-  // column tile gets at least one CTA; at K = 512 only a 3-deep ring would fit and that measured slower than
-  // streaming both operands through a 5-deep ring (2.29 vs 1.80 ms per 1.0 M tokens)
-  int ws_stages = 0;
-  for (int st = G_MAX_STAGES; st >= 5 && !ws_stages; --st)
-    if ((size_t)k_blocks * G_B_BYTES + (size_t)st * G_A_BYTES + 2 * stage_area(true) + misc <= 227 * 1024) ws_stages = st;
-  if (ws_stages && n_tiles <= sm_count() && !(g_debug_flags & (1 << 19))) {
-    const size_t smem_res = (size_t)k_blocks * G_B_BYTES + (size_t)ws_stages * G_A_BYTES + 2 * stage_area(true) + misc;
-    const int per_n = std::max(1, std::min(sm_count() / n_tiles, m_tiles));
-    TTR_CHECK_CUDA(cudaFuncSetAttribute(gemm_bias_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_res));
-    gemm_bias_kernel<true, true><<<n_tiles * per_n, G_THREADS, smem_res, (cudaStream_t)stream>>>(
-        map_a, map_w, map_c, bias, m_bound, m_valid, N, K, g_debug_flags, C16, ws_stages, 2);
-    TTR_CHECK_LAUNCH();
-    return TTR_OK;
-  }
   if (!(g_debug_flags & (1 << 30)) && sm_count() >= 2) {
-    // CTA pairs, 256 x 256 tiles (debug bit 30: the single-CTA 128 x 128 kernel below, for A/B)
-    constexpr int STP = 4;
-    const size_t smem_p = (size_t)STP * G_STAGE_BYTES + 2 * (size_t)G_F16_STAGE + (3 * G_MAX_STAGES + 4) * sizeof(uint64_t) + 16 + 1024;
+    // Default for every K: CTA pairs, 256 x 256 tiles (layer 0, K = 200: 636 vs 523 TFLOP/s for the weight-stationary
+    // single-CTA kernel; layer 1, K = 512: 1,160 vs 727).  Debug bit 30 selects the single-CTA kernels below (A/B).
+    constexpr int STP = GP_STAGES;
+    const size_t smem_p = (size_t)STP * G_STAGE_BYTES + 2 * (size_t)GP_STAGE + (3 * G_MAX_STAGES + 4) * sizeof(uint64_t) + 16 + 1024;
     static thread_local int attr_dev = -1;
     int cur_dev = 0;
     TTR_CHECK_CUDA(cudaGetDevice(&cur_dev));
@@ -590,6 +628,21 @@ extern "C" int ttr_gemm_f16_bias(const void* A16, const void* W16, const float* 
     void* args[] = {(void*)&map_a, (void*)&map_w, (void*)&bias, (void*)&m_bound, (void*)&m_valid, (void*)&N, (void*)&K,
                     (void*)&dbgv, (void*)&c16, (void*)&stp};
     TTR_CHECK_CUDA(cudaLaunchKernelExC(&cfg, (const void*)gemm_bias_pair_kernel, args));
+    return TTR_OK;
+  }
+  // weight-stationary when the W tile fits next to a >= 5-deep A ring and two epilogue groups (K <= 256) and every
+  // column tile gets at least one CTA; at K = 512 only a 3-deep ring would fit and that measured slower than
+  // streaming both operands through a 5-deep ring (2.29 vs 1.80 ms per 1.0 M tokens)
+  int ws_stages = 0;
+  for (int st = G_MAX_STAGES; st >= 5 && !ws_stages; --st)
+    if ((size_t)k_blocks * G_B_BYTES + (size_t)st * G_A_BYTES + 2 * stage_area(true) + misc <= 227 * 1024) ws_stages = st;
+  if (ws_stages && n_tiles <= sm_count() && !(g_debug_flags & (1 << 19))) {
+    const size_t smem_res = (size_t)k_blocks * G_B_BYTES + (size_t)ws_stages * G_A_BYTES + 2 * stage_area(true) + misc;
+    const int per_n = std::max(1, std::min(sm_count() / n_tiles, m_tiles));
+    TTR_CHECK_CUDA(cudaFuncSetAttribute(gemm_bias_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_res));
+    gemm_bias_kernel<true, true><<<n_tiles * per_n, G_THREADS, smem_res, (cudaStream_t)stream>>>(
+        map_a, map_w, map_c, bias, m_bound, m_valid, N, K, g_debug_flags, C16, ws_stages, 2);
+    TTR_CHECK_LAUNCH();
     return TTR_OK;
   }
   constexpr int ST16 = 4;                  // 4 x 32 KB ring + two 34 KB staging groups (1.80 ms per 1.0 M tokens at
