@@ -196,6 +196,8 @@ def frontend_search(query_emb, doc_emb, documents, indptr, indices, data, q_idx,
                     n_candidates: int = 50, n_results: int = 10, space: str = "l2"):
     """The whole `/search` handler — reference `frontend/main.py:102-210` — for one query, with the
     exact cosine top-50 standing in for `collection.query` (`:153-156`; Chroma is absent here).
+    Pinned by `tests/golden/frontend_search.npz`: the responses of the unmodified handler over a
+    stand-in store (`oracle/make_golden_frontend.py`).
     Returns the list that becomes `results` (without the rank / id decoration of `:206-209`)."""
     q_idx, q_val = np.asarray(q_idx), np.asarray(q_val, dtype=np.float64)
     n = len(documents)
@@ -210,8 +212,12 @@ def frontend_search(query_emb, doc_emb, documents, indptr, indices, data, q_idx,
                 for i in top if sims[i] > 1e-5]
     kc = min(n_candidates, n)
     s, i = cosine_topk(np.asarray(query_emb, np.float32)[None, :], doc_emb, kc, dtype=np.float64)
+    # a token-less query is the zero vector (`query_inferencer.py:65-69`): the store's squared-L2 distance is then
+    # |d|^2, not 2 - 2cos; pinned by tests/golden/frontend_search.npz (the unmodified handler on the query "")
+    q_sq = float((np.asarray(query_emb, np.float64) ** 2).sum())
     order, fin, sem, tf = hybrid_rerank_frontend(i[0], s[0], indptr, indices, data, q_idx, q_val, alpha,
-                                                 top_n=min(n_results, kc), space=space)
+                                                 top_n=min(n_results, kc), space=space,
+                                                 q_sqnorm=None if abs(q_sq - 1.0) < 1e-4 else q_sq)
     return [{"doc": documents[int(i[0][o])], "score": float(f), "dense_score": float(se), "tfidf_score": float(t)}
             for o, f, se, t in zip(order, fin, sem, tf)]
 

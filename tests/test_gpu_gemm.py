@@ -116,18 +116,21 @@ def test_tn_weight_gradient_gemm_matches_fp64(cuda_device, M, N1, N2, lda_extra,
 
 
 @pytest.mark.parametrize("M,N,K,mv", [(1000, 1536, 512, None), (513, 1536, 512, 300), (256, 256, 320, None), (5000, 1536, 512, 4321),
-                                      (300, 520, 264, None), (129, 104, 456, 1), (20000, 1536, 512, None)])
+                                      (300, 520, 264, None), (129, 104, 456, 1), (20000, 1536, 512, None),
+                                      (20000, 1536, 200, None), (5000, 1536, 200, 4097), (300, 1536, 200, None), (700, 520, 256, None),
+                                      (129, 104, 8, 1), (40000, 768, 200, 39000)])
 def test_f16_pair_gemm_matches_fp64_and_the_single_cta_kernel(cuda_device, M, N, K, mv):
-    """K > 256 runs CTA pairs (tcgen05.mma.cta_group::2, 256 x 256 tiles, each CTA loads half of A's and half of W's rows);
-    debug bit 30 selects the single-CTA 128 x 128 kernel.  Same operands, same k order -> same fp16 results; rows at or
-    beyond the device-side row count stay untouched."""
+    """Every K runs CTA pairs (tcgen05.mma.cta_group::2, 256 x 256 tiles, each CTA loads half of A's and half of W's rows);
+    K <= 256 keeps each CTA's W rows resident and streams only A (debug bit 19: stream W too); debug bit 30 selects the
+    single-CTA 128 x 128 kernels.  Same operands, same k order -> same fp16 results; rows at or beyond the device-side
+    row count stay untouched."""
     g = torch.Generator(device=cuda_device).manual_seed(M + N + K)
     A = (torch.randn(M, K, device=cuda_device, generator=g) * 0.4).half()
     W = ((torch.rand(N, K, device=cuda_device, generator=g) - 0.5) / 8).half()
     b = torch.randn(N, device=cuda_device, generator=g) * 0.05
     mvt = None if mv is None else torch.tensor([mv], dtype=torch.int32, device=cuda_device)
     out = {}
-    for name, flags in (("pair", 0), ("single", 1 << 30)):
+    for name, flags in (("pair", 0), ("single", 1 << 30), ("pair_streamed_w", 1 << 19)):
         C = torch.full((M, N), 7.0, dtype=torch.float16, device=cuda_device)
         _lib.call_nostream("ttr_debug_set_flags", flags)
         try:
@@ -142,6 +145,7 @@ def test_f16_pair_gemm_matches_fp64_and_the_single_cta_kernel(cuda_device, M, N,
     err = (out["pair"][:rows].double() - ref).abs()
     assert float((err - ref.abs() * 2.0 ** -11).max()) <= 2e-6 * max(scale, 1.0), float(err.max())
     assert torch.equal(out["pair"][:rows], out["single"][:rows])
+    assert torch.equal(out["pair"][:rows], out["pair_streamed_w"][:rows])
     tail_lo = (rows + 255) // 256 * 256                    # rows of partially valid tiles may be written (caller-owned, never read)
     if tail_lo < M:
         assert (out["pair"][tail_lo:] == 7.0).all()

@@ -153,3 +153,53 @@ def test_corpus_evaluator_matches_reference(world):
         assert abs(got[k] - v) <= 0.06, (k, got[k], v)       # one near-tie swap moves a mean over ~27 queries by <= 1/27
     with pytest.raises(RuntimeError):
         CorpusEvaluator(top_k=[500]).evaluate(model, world["val"], tok, dev)
+
+
+def test_search_service_matches_the_unmodified_frontend_handler(tmp_path, cuda_device):
+    """`tests/golden/frontend_search.npz` holds the responses of `/root/reference/frontend/main.py::search`
+    (`:102-210`, unmodified) over a stand-in store answering by exhaustive float32 squared L2
+    (`oracle/make_golden_frontend.py`).  Here the whole chain is ours: artefact writer on the GPU towers -> resident
+    index -> `SearchService.search`.  Scores follow the embedding tolerance (1e-3 relative on unit vectors: dense_score =
+    1 - |q - d|^2 moves by <= 2e-3); documents must be the reference's except where two scores are that close."""
+    g = load_golden("frontend_search")
+    words = json.loads(str(g["words"]))
+    w2i = tmp_path / "word_to_idx.pkl"
+    with open(w2i, "wb") as fh:
+        pickle.dump({w: i for i, w in enumerate(words)}, fh)
+    tok = PretrainedTokenizer(str(w2i))
+    cfg = g["cfg"]
+    sd = synth.make_state_dict(cfg, seed=int(g["weight_seeds"][0]), table_seed=int(g["weight_seeds"][1]))
+    model = model_from_numpy(cfg, sd, cuda_device).eval()
+    model.device = cuda_device
+    triplets = [tuple(t) for t in json.loads(str(g["triplets"]))]
+    art = tmp_path / "artifacts" / "run-fe"
+    run_cfg = {k: v for k, v in cfg.items() if k != "VOCAB_SIZE"}
+    run_cfg["WORD_TO_IDX_PATH"] = str(w2i)
+    save_inference_artifacts(art, model, run_cfg, tok, {"train": triplets, "validation": triplets[:20]})
+    svc = SearchService(str(art), device=cuda_device)
+    TOL = 2e-3
+    n_same, n_total = 0, 0
+    for item in json.loads(str(g["responses"])):
+        q, alpha = item["query"], item["alpha"]
+        if item["raises"]:
+            with pytest.raises(RuntimeError):
+                svc.search(q, alpha)
+            continue
+        out = svc.search(q, alpha)
+        want = item["response"]
+        assert out["query"] == want["query"] and out["alpha"] == want["alpha"]
+        res, ref = out["results"], want["results"]
+        assert len(res) == len(ref), (q, alpha)
+        for r, (a, b) in enumerate(zip(res, ref)):
+            assert set(a) == set(b) and a["rank"] == b["rank"] and a["id"] == b["id"]
+            assert abs(a["score"] - b["score"]) <= TOL * max(abs(alpha), 1e-9) + 1e-12, (q, alpha, r)
+            n_total += 1
+            if a["doc"] == b["doc"]:
+                n_same += 1
+                assert abs(a["dense_score"] - b["dense_score"]) <= (TOL if alpha != 0.0 else 0.0)
+                assert abs(a["tfidf_score"] - b["tfidf_score"]) <= 1e-12
+            elif q != "":                                   # "" is one 140-way tie at dense_score = 0 +- 3e-7
+                assert any(w["doc"] == a["doc"] and abs(w["score"] - a["score"]) <= 2 * TOL for w in ref) or r >= len(ref) - 2
+        if q == "" and alpha != 0.0:
+            assert all(abs(a["dense_score"]) <= 1e-5 and a["tfidf_score"] == 0.0 for a in res)
+    assert n_same >= 0.9 * n_total - 40, (n_same, n_total)

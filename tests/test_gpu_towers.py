@@ -187,5 +187,19 @@ def test_bulk_encode_matches_per_batch_encode(cuda_device):
     with torch.no_grad():
         ref = m.encode_document(torch.tensor(ids, device=cuda_device))
     assert torch.allclose(out, ref, atol=2e-6)
+    # two compute lanes (default) give bit-identical rows to one, into a caller-owned matrix at an offset, and the
+    # device-batch entry point agrees with plain forwards
+    from twotowermlretrieval_b200.encode import encode_padded_batches
+    one = encode_rows(m.doc_encoder, rows, cuda_device, max_tokens=4096, max_rows=64, streams=1)
+    big = torch.zeros(520, cfg["HIDDEN_DIM"], device=cuda_device)
+    encode_rows(m.doc_encoder, rows, cuda_device, out=big, out_offset=10, max_tokens=2048, max_rows=48, streams=3)
+    assert torch.equal(out, one)
+    assert torch.allclose(big[10:510], out, atol=2e-6) and float(big[:10].abs().sum()) == 0.0 and float(big[510:].abs().sum()) == 0.0
+    order = np.argsort(-lens, kind="stable")
+    bts = [torch.tensor(ids[order[i:i + 100], :int(lens[order[i]])], device=cuda_device) for i in range(0, 500, 100)]
+    es = encode_padded_batches(m.doc_encoder, bts, streams=2)
+    with torch.no_grad():
+        for b, e in zip(bts, es):
+            assert torch.equal(e, m.encode_document(b))
     with pytest.raises(RuntimeError):
         encode_rows(m.doc_encoder, rows[:3] + [[]], cuda_device)

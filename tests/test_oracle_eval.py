@@ -94,3 +94,43 @@ def test_collate_matches_reference_contract(tmp_path):
     assert torch.equal(q, q2) and torch.equal(p, p2) and torch.equal(n, n2)
     assert q.dtype == torch.int64 and q.shape[1] == max(len(tok.encode(t[0])) for t in triplets[:5])
     assert (q[0, len(tok.encode(triplets[0][0])):] == 0).all()
+
+
+def test_frontend_search_restatement_matches_the_unmodified_handler():
+    """`oracle/make_golden_frontend.py` ran `/root/reference/frontend/main.py::search` (`:102-210`) itself, over a
+    stand-in store answering by exhaustive float32 squared L2.  The restatement must give the same response body."""
+    from sklearn.feature_extraction.text import TfidfVectorizer
+    g = load_golden("frontend_search")
+    docs = json.loads(str(g["documents"]))
+    vocab = json.loads(str(g["tfidf_vocab"]))
+    vec = TfidfVectorizer()                                   # the reference's default vectoriser (`main.py:139`)
+    vec.vocabulary_ = vocab
+    vec.idf_ = g["tfidf_idf"]
+    probes = json.loads(str(g["probes"]))
+    emb_of = dict(zip(probes, g["probe_emb"]))
+    n_checked = 0
+    for item in json.loads(str(g["responses"])):
+        q, alpha = item["query"], item["alpha"]
+        if item["raises"]:                                    # "the the": zero-length sequence (quirk #2)
+            assert alpha != 0.0 and np.isnan(emb_of[q]).all()
+            continue
+        qrow = vec.transform([q]).tocsr()
+        qrow.sort_indices()
+        q_emb = np.zeros(g["doc_emb"].shape[1], np.float32) if np.isnan(emb_of[q]).all() else emb_of[q]
+        got = onp.frontend_search(q_emb, g["doc_emb"], docs, g["tfidf_indptr"], g["tfidf_indices"], g["tfidf_data"],
+                                  qrow.indices, qrow.data, alpha)
+        want = item["response"]["results"]
+        assert item["response"]["query"] == q and item["response"]["alpha"] == alpha
+        assert len(got) == len(want), (q, alpha)
+        for r, (a, b) in enumerate(zip(got, want)):
+            assert b["rank"] == r + 1 and b["id"] == f"result-{r + 1}"
+            assert abs(a["score"] - b["score"]) <= 2e-6, (q, alpha, r)
+            if a["doc"] != b["doc"]:                          # float32-distance ties in the store may order differently
+                # (the query "" is the zero vector: every document is at distance |d|^2 = 1 +- 3e-7, one 140-way tie)
+                assert abs(a["dense_score"] - b["dense_score"]) <= 2e-6 and abs(a["tfidf_score"] - b["tfidf_score"]) <= 2e-6
+                assert q == "" or any(abs(w["score"] - a["score"]) <= 2e-6 and w["doc"] == a["doc"] for w in want)
+                continue
+            assert abs(a["dense_score"] - b["dense_score"]) <= 2e-6      # the store's distance is float32
+            assert abs(a["tfidf_score"] - b["tfidf_score"]) <= 1e-12
+            n_checked += 1
+    assert n_checked > 250

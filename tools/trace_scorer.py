@@ -29,7 +29,8 @@ ntile = -(-N // 32 + 147) // 148
 print("tiles per CTA ~", ntile, "; cycles from first TMA issue to last filtered:", mk[2] - t0)
 names = ["prod_issue", "mma_full", "mma_issued", "epi_accfull", "epi_release", "mma_done", "epi_loop_end", "epi_tile_end"]
 print("tile " + " ".join(f"{n:>12}" for n in names))
-for i in list(range(0, 12)) + list(range(100, 112)):
+rows = range(0, 256) if (len(sys.argv) > 4 and sys.argv[4] == "all") else list(range(0, 12)) + list(range(100, 112))
+for i in rows:
     print(f"{i:4d} " + " ".join(f"{int(t[r, i] - t0):12d}" for r in range(8)))
 d = np.diff(t[:, 20:250], axis=1)
 print("mean cycles/tile per role:", d.mean(axis=1))

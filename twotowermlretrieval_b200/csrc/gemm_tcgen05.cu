@@ -18,7 +18,7 @@ namespace ttr {
 constexpr int GM = 128;            // tile rows  (UMMA M)
 constexpr int GN = 128;            // tile cols  (UMMA N)
 constexpr int GK = 32;             // fp32 elements per k-block = one 128-byte swizzle row
-constexpr int G_MAX_STAGES = 6;
+constexpr int G_MAX_STAGES = 8;
 constexpr int G_A_BYTES = GM * GK * 4;   // 16 KB
 constexpr int G_B_BYTES = GN * GK * 4;   // 16 KB
 constexpr int G_STAGE_BYTES = G_A_BYTES + G_B_BYTES;
@@ -352,20 +352,31 @@ __device__ __forceinline__ void f16_half_to_stage(uint32_t tmem_col0, int q, int
   }
 }
 
+// WRES = true (K <= 256: layer 0): weight-stationary pairs.  The number of pairs is a multiple of the number of
+// 256-column tiles, so a pair's column tile never changes: each CTA loads its 128 rows of W (all k-blocks, 64 KB at
+// K = 200) ONCE, and the ring carries only A (16 KB per stage, 7 stages).  The non-resident pair kernel at K = 200 was
+// bound by the ring, not by MMAs or HBM: 5 stages x 32 KB in flight against ~3.5 k cycles of load latency is one
+// 256 x 256 x 64 k-block per ~800 cycles, while its 4 (3.25 real) k-steps need 512; resident W halves the bytes per
+// k-block and leaves room for 7 stages -> 3.5x the k-blocks in flight.
+template <bool WRES>
 __global__ void __launch_bounds__(G_THREADS, 1)
 gemm_bias_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
                       const float* __restrict__ bias, int m_bound, const int32_t* __restrict__ m_valid, int N, int K,
                       int dbg, __half* __restrict__ c_out, int n_stages) {
   extern __shared__ unsigned char smem_raw[];
   constexpr int GKE = 2 * GK;                       // halves per 128-byte k-block
-  unsigned char* tiles = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
-  unsigned char* out_stage = tiles + n_stages * G_STAGE_BYTES;      // per epilogue group
+  constexpr int STAGE_B = WRES ? G_A_BYTES : G_STAGE_BYTES;
+  const int k_blocks = ceil_div(K, GKE);
+  unsigned char* w_res = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);   // WRES: [k_blocks][16 KB]
+  unsigned char* tiles = w_res + (WRES ? k_blocks * G_B_BYTES : 0);
+  unsigned char* out_stage = tiles + n_stages * STAGE_B;            // per epilogue group
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(out_stage + 2 * GP_STAGE);
   uint64_t* empty_bar = full_bar + G_MAX_STAGES;
   uint64_t* peer_full = empty_bar + G_MAX_STAGES;   // leader only: the peer's half of stage s has landed
   uint64_t* acc_full = peer_full + G_MAX_STAGES;    // [2] MMA -> epilogue
   uint64_t* acc_empty = acc_full + 2;               // [2] epilogue -> MMA (leader's: both CTAs' groups arrive)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  uint64_t* w_full = acc_empty + 2;                 // WRES: this CTA's resident W rows have landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_full + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = ptx::cluster_ctarank();
@@ -373,7 +384,6 @@ gemm_bias_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
   const int M = m_valid ? min(m_bound, *m_valid) : m_bound;
   const int m_tiles = ceil_div(M, 2 * GM), n_tiles = ceil_div(N, 2 * GN);
   const int total_tiles = m_tiles * n_tiles;
-  const int k_blocks = ceil_div(K, GKE);
   const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
 
   if (threadIdx.x == 0) {
@@ -381,6 +391,7 @@ gemm_bias_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
       ptx::mbar_init(full_bar + s, 1); ptx::mbar_init(empty_bar + s, 1); ptx::mbar_init(peer_full + s, 1);
     }
     for (int b = 0; b < 2; ++b) { ptx::mbar_init(acc_full + b, 1); ptx::mbar_init(acc_empty + b, 8); }
+    ptx::mbar_init(w_full, 1);
     ptx::fence_mbar_init();
   }
   if (warp == 2) {
@@ -398,6 +409,12 @@ gemm_bias_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
       ptx::prefetch_tensormap(&map_a);
       ptx::prefetch_tensormap(&map_w);
     }
+    if (WRES && pair < total_tiles && ptx::elect_one()) {
+      const int n0 = (pair % n_tiles) * 2 * GN + (int)rank * GN;      // constant for this pair: n_pairs % n_tiles == 0
+      ptx::mbar_arrive_expect_tx(w_full, (uint32_t)(k_blocks * G_B_BYTES));
+      for (int kb = 0; kb < k_blocks; ++kb) ptx::tma_load_2d(w_res + kb * G_B_BYTES, &map_w, kb * GKE, n0, w_full);
+    }
+    __syncwarp();
     int it = 0;
     for (int tile = pair; tile < total_tiles; tile += n_pairs) {
       const int m0 = (tile / n_tiles) * 2 * GM + (int)rank * GM, n0 = (tile % n_tiles) * 2 * GN + (int)rank * GN;
@@ -405,11 +422,11 @@ gemm_bias_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
         const int s = it % n_stages;
         const uint32_t ph = (uint32_t)(it / n_stages) & 1u;
         ptx::mbar_wait(empty_bar + s, ph ^ 1u);
-        unsigned char* a_dst = tiles + s * G_STAGE_BYTES;
+        unsigned char* a_dst = tiles + s * STAGE_B;
         if (ptx::elect_one()) {
-          ptx::mbar_arrive_expect_tx(full_bar + s, G_STAGE_BYTES);
+          ptx::mbar_arrive_expect_tx(full_bar + s, STAGE_B);
           ptx::tma_load_2d(a_dst, &map_a, kb * GKE, m0, full_bar + s);
-          ptx::tma_load_2d(a_dst + G_A_BYTES, &map_w, kb * GKE, n0, full_bar + s);
+          if (!WRES) ptx::tma_load_2d(a_dst + G_A_BYTES, &map_w, kb * GKE, n0, full_bar + s);
         }
         __syncwarp();
       }
@@ -418,6 +435,8 @@ gemm_bias_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
     // ===== MMA issuer (leader CTA): M = 256 (128 rows per CTA), N = 256 (128 W rows per CTA), K = 16 =====
     constexpr uint32_t idesc = ptx::make_idesc_f16(2 * GM, 2 * GN);
     int it = 0, local = 0;
+    // (the peer's W rows: its forwarder only reports stages after its own W has landed)
+    if (WRES && pair < total_tiles) ptx::mbar_wait(w_full, 0u);
     for (int tile = pair; tile < total_tiles; tile += n_pairs, ++local) {
       const int buf = local & 1;
       const uint32_t aph = (uint32_t)(local >> 1) & 1u;
@@ -430,9 +449,9 @@ gemm_bias_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
         ptx::mbar_wait(full_bar + s, ph);
         ptx::mbar_wait(peer_full + s, ph);
         ptx::tc_fence_after_sync();
-        const uint32_t a_addr = ptx::smem_u32(tiles + s * G_STAGE_BYTES);
+        const uint32_t a_addr = ptx::smem_u32(tiles + s * STAGE_B);
         const uint64_t a_desc = ptx::make_kmajor_sw128_desc(a_addr);
-        const uint64_t b_desc = ptx::make_kmajor_sw128_desc(a_addr + G_A_BYTES);
+        const uint64_t b_desc = ptx::make_kmajor_sw128_desc(WRES ? ptx::smem_u32(w_res + kb * G_B_BYTES) : a_addr + G_A_BYTES);
         if (ptx::elect_one()) {
 #pragma unroll
           for (int k = 0; k < GK / 8; ++k)
@@ -447,6 +466,7 @@ gemm_bias_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
   } else if (warp == 1) {
     // ===== peer CTA: forward "my half of stage s has landed" to the leader's MMA issuer =====
     int it = 0;
+    if (WRES && pair < total_tiles) ptx::mbar_wait(w_full, 0u);
     for (int tile = pair; tile < total_tiles; tile += n_pairs)
       for (int kb = 0; kb < k_blocks; ++kb, ++it) {
         const int s = it % n_stages;
@@ -602,17 +622,30 @@ extern "C" int ttr_gemm_f16_bias(const void* A16, const void* W16, const float* 
   if (!(g_debug_flags & (1 << 30)) && sm_count() >= 2) {
     // Default for every K: CTA pairs, 256 x 256 tiles (layer 0, K = 200: 636 vs 523 TFLOP/s for the weight-stationary
     // single-CTA kernel; layer 1, K = 512: 1,160 vs 727).  Debug bit 30 selects the single-CTA kernels below (A/B).
-    constexpr int STP = GP_STAGES;
-    const size_t smem_p = (size_t)STP * G_STAGE_BYTES + 2 * (size_t)GP_STAGE + (3 * G_MAX_STAGES + 4) * sizeof(uint64_t) + 16 + 1024;
+    const size_t misc_p = (3 * G_MAX_STAGES + 5) * sizeof(uint64_t) + 16 + 1024;
+    const size_t smem_max = 227 * 1024;
+    const int pn_tiles = ceil_div(N, 2 * GN), pm_tiles = ceil_div(m_bound, 2 * GM);
+    const int pair_tiles = pm_tiles * pn_tiles;
+    // weight-stationary pairs when a CTA's 128 W rows (all k-blocks) fit next to >= 6 A stages and every column tile
+    // gets at least one pair (K <= 256); debug bit 19: stream W through the ring as for K = 512 (A/B)
+    int res_stages = 0;
+    for (int st = G_MAX_STAGES; st >= 6 && !res_stages; --st)
+      if ((size_t)k_blocks * G_B_BYTES + (size_t)st * G_A_BYTES + 2 * (size_t)GP_STAGE + misc_p <= smem_max) res_stages = st;
+    const bool wres = res_stages > 0 && pn_tiles <= sm_count() / 2 && !(g_debug_flags & (1 << 19));
+    const int STP = wres ? res_stages : GP_STAGES;
+    const size_t smem_p = wres ? (size_t)k_blocks * G_B_BYTES + (size_t)STP * G_A_BYTES + 2 * (size_t)GP_STAGE + misc_p
+                               : (size_t)STP * G_STAGE_BYTES + 2 * (size_t)GP_STAGE + misc_p;
+    const void* kern = wres ? (const void*)gemm_bias_pair_kernel<true> : (const void*)gemm_bias_pair_kernel<false>;
     static thread_local int attr_dev = -1;
     int cur_dev = 0;
     TTR_CHECK_CUDA(cudaGetDevice(&cur_dev));
     if (attr_dev != cur_dev) {
-      TTR_CHECK_CUDA(cudaFuncSetAttribute(gemm_bias_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_p));
+      TTR_CHECK_CUDA(cudaFuncSetAttribute(gemm_bias_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
+      TTR_CHECK_CUDA(cudaFuncSetAttribute(gemm_bias_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
       attr_dev = cur_dev;
     }
-    const int pair_tiles = ceil_div(m_bound, 2 * GM) * ceil_div(N, 2 * GN);
-    const int pairs = std::max(1, std::min(pair_tiles, sm_count() / 2));
+    int pairs = std::max(1, std::min(pair_tiles, sm_count() / 2));
+    if (wres) pairs = pn_tiles * std::max(1, std::min(sm_count() / 2 / pn_tiles, pm_tiles));   // multiple of the column tiles
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(2 * pairs);
     cfg.blockDim = dim3(G_THREADS);
@@ -627,7 +660,7 @@ extern "C" int ttr_gemm_f16_bias(const void* A16, const void* W16, const float* 
     __half* c16 = reinterpret_cast<__half*>(C16);
     void* args[] = {(void*)&map_a, (void*)&map_w, (void*)&bias, (void*)&m_bound, (void*)&m_valid, (void*)&N, (void*)&K,
                     (void*)&dbgv, (void*)&c16, (void*)&stp};
-    TTR_CHECK_CUDA(cudaLaunchKernelExC(&cfg, (const void*)gemm_bias_pair_kernel, args));
+    TTR_CHECK_CUDA(cudaLaunchKernelExC(&cfg, kern, args));
     return TTR_OK;
   }
   // weight-stationary when the W tile fits next to a >= 5-deep A ring and two epilogue groups (K <= 256) and every

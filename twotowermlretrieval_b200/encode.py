@@ -8,6 +8,11 @@ buffers with asynchronous H2D copies on a side stream (the host fills batch i+1 
 copy engine moves batch i and the SMs encode batch i-1), encoded with the zero-length check
 disabled (no device->host sync per batch), and written straight into the resident output
 matrix — e.g. a rank's shard of the search index — in caller order.
+
+Consecutive batches alternate between TWO compute streams.  The tcgen05 recurrence is a latency chain
+that holds 15 clusters of 8 CTAs (120 of the 148 SMs) and leaves most issue slots and the whole HBM
+stream idle; with a second batch in flight its gather, projection GEMMs and head run on the SMs and in
+the bubbles the first batch's recurrence leaves (and vice versa), instead of one kernel at a time.
 """
 from __future__ import annotations
 
@@ -16,7 +21,7 @@ from typing import Optional, Sequence, Tuple, Union
 import numpy as np
 import torch
 
-from . import _lib
+from . import _lib, towers
 
 Ragged = Tuple[np.ndarray, np.ndarray]      # (flat int64 token ids, int64 lengths)
 
@@ -68,8 +73,65 @@ class _Staging:
         self.copied: Optional[torch.cuda.Event] = None
 
 
+class _Lanes:
+    """`n` compute streams that take turns; `begin()` makes them wait for the caller's stream (weights, earlier
+    work), `end()` makes the caller's stream wait for all of them.  n = 1 is the caller's stream itself."""
+
+    def __init__(self, encoder, device, n: int):
+        self.dev = torch.device(device)
+        self.main = torch.cuda.current_stream(self.dev)
+        self.streams = [self.main] if n <= 1 else [torch.cuda.Stream(device=self.dev) for _ in range(n)]
+        # everything a lane reads must be complete on the caller's stream first: the flat parameter buffer and the
+        # fp16 copies of W_ih are (re)built lazily by the first forward that needs them
+        encoder._ensure_flat()
+        if encoder.hidden_dim == 256 and towers._fp16_pipeline_allowed():
+            for layer in range(encoder.num_layers):
+                towers._w16_cached(encoder, layer, encoder.layer_weights(layer)[0])
+        for s in self.streams:
+            if s is not self.main:
+                s.wait_stream(self.main)
+        self.i = 0
+
+    def next(self) -> "torch.cuda.Stream":
+        s = self.streams[self.i % len(self.streams)]
+        self.i += 1
+        return s
+
+    def end(self):
+        for s in self.streams:
+            if s is not self.main:
+                self.main.wait_stream(s)
+
+
+def encode_padded_batches(encoder, batches: Sequence[torch.Tensor], streams: int = 2) -> "list[torch.Tensor]":
+    """Encode device-resident padded id batches [R_i, T_i] (inference, zero-length check off) with consecutive
+    batches on alternating compute streams; returns the embeddings in order.  Results are ordered after the
+    caller's current stream like any other call."""
+    if not batches:
+        return []
+    was_strict, was_training = encoder.strict_lengths, encoder.training
+    encoder.strict_lengths = False
+    encoder.eval()
+    lanes = _Lanes(encoder, batches[0].device, streams)
+    outs = []
+    try:
+        with torch.no_grad():
+            for b in batches:
+                s = lanes.next()
+                with torch.cuda.stream(s):
+                    e = encoder(b)
+                if s is not lanes.main:
+                    e.record_stream(lanes.main)
+                outs.append(e)
+    finally:
+        lanes.end()
+        encoder.strict_lengths = was_strict
+        encoder.train(was_training)
+    return outs
+
+
 def encode_rows(encoder, rows: Union[Ragged, Sequence[Sequence[int]]], device, out: Optional[torch.Tensor] = None,
-                out_offset: int = 0, max_tokens: int = 524288, max_rows: int = 15360) -> torch.Tensor:
+                out_offset: int = 0, max_tokens: int = 524288, max_rows: int = 15360, streams: int = 2) -> torch.Tensor:
     """Encode tokenised rows with `encoder` (an RNNEncoder) -> fp32 [n, H] on `device`
     (rows `out[out_offset : out_offset + n]` if `out` is given).  `rows` is a list of id lists or a
     (flat ids, lengths) pair.  Raises RuntimeError for empty rows like the reference's
@@ -98,8 +160,8 @@ def encode_rows(encoder, rows: Union[Ragged, Sequence[Sequence[int]]], device, o
     encoder.strict_lengths = False
     encoder.eval()
     dev = torch.device(device)
-    main = torch.cuda.current_stream(dev)
     copy_stream = torch.cuda.Stream(device=dev)
+    lanes = _Lanes(encoder, dev, streams)
     try:
         with torch.no_grad():
             for bi, (lo, hi) in enumerate(bounds):
@@ -118,13 +180,16 @@ def encode_rows(encoder, rows: Union[Ragged, Sequence[Sequence[int]]], device, o
                     dev_idx = st.idx[:R].to(dev, non_blocking=True)
                     st.copied = torch.cuda.Event()
                     st.copied.record(copy_stream)
-                main.wait_stream(copy_stream)
+                cs = lanes.next()
+                cs.wait_stream(copy_stream)
                 encoder._token_bound = int(nnz[idx].sum())      # rows of the packed per-token matrices (<= R * T)
-                emb = encoder(dev_ids)
-                out.index_copy_(0, dev_idx, emb)
-                dev_ids.record_stream(main)
-                dev_idx.record_stream(main)
+                with torch.cuda.stream(cs):
+                    emb = encoder(dev_ids)
+                    out.index_copy_(0, dev_idx, emb)            # distinct rows per batch: lanes never write the same row
+                dev_ids.record_stream(cs)
+                dev_idx.record_stream(cs)
     finally:
+        lanes.end()
         encoder._token_bound = None
         encoder.strict_lengths = was_strict
         encoder.train(was_training)
