@@ -837,8 +837,8 @@ def bar_encode(c, cfg, batches, n_pass):
 def leg_train(c, cpu_ok, per_gpu: int = 1024):
     """BASELINE configs[4]: one data-parallel step = 3 encodes + cosine triplet loss + backward + all-reduce of the flat
     16 MB gradient bucket + fused clip(1.0) + Adam (backend/main.py:244-259), 1024 triplets per GPU."""
-    from twotowermlretrieval_b200 import TwoTowerModel, synth, triplet_loss_cosine
-    from twotowermlretrieval_b200.optim import FusedClipAdam
+    from twotowermlretrieval_b200 import TwoTowerModel, synth
+    from twotowermlretrieval_b200.trainer import TrainerFactory
     cfg = synth.default_config()
     cfg["DROPOUT"] = 0.0                                   # deterministic step (train-mode dropout timing differs by one small kernel)
     sd = synth.make_state_dict(cfg, seed=0, table_seed=1)
@@ -846,30 +846,34 @@ def leg_train(c, cpu_ok, per_gpu: int = 1024):
     model.load_state_dict({k: torch.tensor(v) for k, v in sd.items()})
     model.to(c.dev).train()
     model.query_encoder.strict_lengths = model.doc_encoder.strict_lengths = False
-    opt = FusedClipAdam(model, lr=cfg["LR"], max_norm=1.0)
+    # the public step: TwoTowerTrainer.train_step = 3 encodes (three tower streams) -> loss -> backward -> all-reduce ->
+    # fused clip + Adam
+    trainer = TrainerFactory.create_trainer(cfg, model, c.dev, fused=True, clip_max_norm=1.0)
     V = cfg["VOCAB_SIZE"]
     t = [torch.tensor(synth.make_tokens(per_gpu, kind, V, seed=31 + j + 10 * c.rank)[0], device=c.dev)
          for j, kind in enumerate(("query", "passage", "passage"))]
     ntok = int(sum((x != 0).sum() for x in t))
 
     def step(s):
-        opt.zero_grad()
-        loss = triplet_loss_cosine((model.encode_query(t[0]), model.encode_document(t[1]), model.encode_document(t[2])),
-                                   margin=cfg["MARGIN"])
-        loss.backward()
-        opt.step()
-        return loss
+        return trainer.train_step(*t)[0]
 
     for s in range(2):
         step(s)
     ms = c.timed(step, 5)
+    lanes = trainer.tower_streams
+    trainer.tower_streams = 1
+    step(0)
+    ms_one = c.timed(step, 5)
+    trainer.tower_streams = lanes
     # verification: every rank holds the same parameters after the all-reduced steps; loss is finite
     same = same_on_all_ranks(c, model.flat_params())
     finite = bool(torch.isfinite(step(0)))
     flops = ntok * 11.3e6
     leg = {"triplets_per_s": per_gpu * c.world * 1e3 / ms, "ms_per_step": ms, "triplets_per_gpu": per_gpu, "n_gpus": c.world,
            "global_batch": per_gpu * c.world, "tokens_per_gpu": ntok, "algorithmic_tflops_per_gpu": flops / (ms * 1e-3) / 1e12,
-           "allreduce_bytes": int(model.flat_grads().numel() * 4), "verified": same and finite,
+           "allreduce_bytes": int(model.flat_grads().numel() * 4), "tower_streams": lanes,
+           "one_stream": {"ms_per_step": ms_one, "triplets_per_s": per_gpu * c.world * 1e3 / ms_one},
+           "verified": same and finite,
            "verification": {"parameters_identical_on_all_ranks": same, "loss_finite": finite},
            "roofline": {"bound": "tensor", "achieved": flops / (ms * 1e-3) / 1e12, "peak": float(c.peaks.get("bf16_tflops", 1667.1)),
                         "unit": "TFLOP/s", "frac": flops / (ms * 1e-3) / 1e12 / float(c.peaks.get("bf16_tflops", 1667.1)),

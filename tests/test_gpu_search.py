@@ -260,7 +260,8 @@ def test_id_segments_and_fast_reject(cuda_device, B, N):
     s_a, i_a = search_topk(Q, D, 50)
     # bit 27: one CTA per query tile (round-1 layout) instead of CTA pairs for B > 128
     for flags in (1 << 24, (1 << 24) | (1 << 21), 1 << 25, (1 << 24) | (1 << 25), 1 << 21, 1 << 27, (1 << 27) | (1 << 24),
-                  1 << 29, (1 << 29) | (1 << 24), (1 << 29) | (1 << 21)):     # bit 29: no screening warps
+                  1 << 29, (1 << 29) | (1 << 24), (1 << 29) | (1 << 21),     # bit 29: no screening warps
+                  -(1 << 31), -(1 << 31) | (1 << 24), -(1 << 31) | (1 << 21)):  # bit 31: no survivor-histogram bound
         _lib.call_nostream("ttr_debug_set_flags", flags)
         try:
             s_b, i_b = search_topk(Q, D, 50)
@@ -285,6 +286,38 @@ def test_adversarial_order_across_segments(cuda_device):
     finally:
         _lib.call_nostream("ttr_debug_set_flags", 0)
     _check_vs_fp64(s[:8], i[:8], Qd[:8], Dd, 50)
+
+
+@pytest.mark.parametrize("B", [128, 256, 40])
+def test_survivor_histogram_bound_is_only_a_pruning_device(cuda_device, B):
+    """The main pass counts every surviving candidate in a per-query histogram above the seeded bound; two idle warps per
+    CTA turn it into a k-th-best lower bound shared by all CTAs (debug bit 31 switches it off).  It must never change
+    the result — also when the score distribution defeats the bin placement: a heavy cluster far above the sample's
+    maximum (everything lands in the open top bin), thousands of exact duplicates of the best documents (plateaus at
+    the bound), scores that all fall into bin 0, and negative / tiny scores."""
+    from twotowermlretrieval_b200 import _lib
+    N = 600_000
+    rng = np.random.default_rng(100 + B)
+    Q = synth.make_unit_rows(B, 256, seed=7 + B)
+    D = synth.make_unit_rows(N, 256, seed=8 + B)
+    D[400_000:400_300] = 0.9 * Q[0] + 0.1 * D[400_000:400_300]           # 300 documents far above anything sampled (query 0)
+    D[500_000:503_000] = D[123]                                          # 3,000 exact duplicates
+    D[550_000:550_040] = Q[1 % B]                                        # 40 perfect matches of query 1: fewer than k
+    D[10_000:20_000] *= 1e-3                                             # tiny scores
+    D[30_000:40_000] *= -1.0
+    Qd, Dd = torch.tensor(Q, device=cuda_device), torch.tensor(D, device=cuda_device)
+    s_a, i_a = search_topk(Qd, Dd, 50)
+    for flags in (-(1 << 31), 1 << 21, -(1 << 31) | (1 << 21)):
+        _lib.call_nostream("ttr_debug_set_flags", flags)
+        try:
+            s_b, i_b = search_topk(Qd, Dd, 50)
+        finally:
+            _lib.call_nostream("ttr_debug_set_flags", 0)
+        assert torch.equal(s_a, s_b) and torch.equal(i_a, i_b), f"flags {flags:#x}"
+    _check_vs_fp64(s_a[:12], i_a[:12], Qd[:12], Dd, 50)
+    for _ in range(3):
+        s_c, i_c = search_topk(Qd, Dd, 50)
+        assert torch.equal(s_a, s_c) and torch.equal(i_a, i_c)
 
 
 def test_concurrent_streams_do_not_share_scratch(cuda_device):

@@ -21,13 +21,13 @@ n, nl = synth.make_tokens(B, "passage", cfg["VOCAB_SIZE"], seed=4)
 qd, pd_, nd = (torch.tensor(a, device=dev) for a in (q, p, n))
 toks = int(ql.sum() + pl.sum() + nl.sum())
 
+from twotowermlretrieval_b200.trainer import TwoTowerTrainer
+LANES = int(sys.argv[2]) if len(sys.argv) > 2 else 3
+trainer = TwoTowerTrainer(model, opt, lambda tr: triplet_loss_cosine(tr, margin=cfg["MARGIN"]), dev, dict(cfg, TOWER_STREAMS=LANES))
+print(f"tower streams: {LANES}")
+
 def step():
-    opt.zero_grad()
-    loss = triplet_loss_cosine((model.encode_query(qd), model.encode_document(pd_), model.encode_document(nd)),
-                               margin=cfg["MARGIN"])
-    loss.backward()
-    opt.step()
-    return loss
+    return trainer.train_step(qd, pd_, nd)[0]
 
 for _ in range(2): step()
 torch.cuda.synchronize()

@@ -623,7 +623,7 @@ extern "C" int ttr_gemm_f16_bias(const void* A16, const void* W16, const float* 
     // Default for every K: CTA pairs, 256 x 256 tiles (layer 0, K = 200: 636 vs 523 TFLOP/s for the weight-stationary
     // single-CTA kernel; layer 1, K = 512: 1,160 vs 727).  Debug bit 30 selects the single-CTA kernels below (A/B).
     const size_t misc_p = (3 * G_MAX_STAGES + 5) * sizeof(uint64_t) + 16 + 1024;
-    const size_t smem_max = 227 * 1024;
+    const size_t smem_max = 227 * 1024 - 2048;          // the kernel also has 2 KB of static shared memory (bias slices)
     const int pn_tiles = ceil_div(N, 2 * GN), pm_tiles = ceil_div(m_bound, 2 * GM);
     const int pair_tiles = pm_tiles * pn_tiles;
     // weight-stationary pairs when a CTA's 128 W rows (all k-blocks) fit next to >= 6 A stages and every column tile

@@ -44,7 +44,12 @@ constexpr int SM_KB = 8;                   // k-blocks of 32 floats
 constexpr int SM_STAGES = 4;
 constexpr int SM_D_KB_BYTES = SM_ND * 128;              // one k-block of a doc tile: 4 KB
 constexpr int SM_STAGE_BYTES = SM_ND * SM_DIM * 4;      // 32 KB
-constexpr int SM_NACC = 4;                              // TMEM accumulator buffers (tiles in flight)
+constexpr int SM_NACC_MAX = 8;                          // TMEM accumulator buffers (tiles in flight): 8 x 32 columns next to the
+                                                        // 256 query columns for single CTAs, 4 x 64 for CTA pairs.  With 4 a burst of
+                                                        // tiles with survivors (a keeper needs ~1,400 cycles for one, a tile arrives
+                                                        // every ~1,000) stalled the MMA issuer and through it the TMA ring: 1,320 cycles
+                                                        // per tile on a 1.1 M-document shard, where the seeded bound stays loose for the
+                                                        // whole scan (~4 survivors per tile) — profiles/r2_scorer_small_shard.md
 constexpr int SM_KSPLIT = 1;                            // accumulation chains per tile (1: no split; the MMA
                                                         // probe shows dependent chains are not slower)
 constexpr int SM_ACC_COLS = SM_KSPLIT * SM_ND;          // columns per buffer: partial sums x 32 docs
@@ -182,18 +187,37 @@ constexpr int SM_TRACE_TILES = 256;   // trace buffer: 8 roles x 256 tiles
       trace[(role) * SM_TRACE_TILES + _ti] = clock64();                                         \
   } while (0)
 
-__global__ void init_tau_kernel(float* tau, int32_t* qcount, int n, unsigned int* counters) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) { tau[i] = -INFINITY; qcount[i] = 0; }
+// Survivor histogram (main pass, seeded searches): SM_HBINS linear bins per query above the seeded bound.  Every
+// candidate a keeper appends is counted (one fire-and-forget atomic) in the bin of its score; the lower edge of the
+// highest bin whose suffix count reaches k is a lower bound on the final k-th best that tightens while ALL CTAs scan,
+// not only when one CTA's own list fills.  On a small shard (233 tiles per CTA at 1.1 M documents) a list never fills:
+// the bound stayed where the sample put it (top 0.1 %) and ~4 documents per tile survived to the keepers, which
+// then set the tile rate (r2 trace: 1,320 cycles per tile against 1,000 of HBM time; CTA pairs 2,430 against 1,415).
+constexpr int SM_HBINS = 64;
+// bins of query q: [lo + b * w, lo + (b + 1) * w), the last one open-ended; w = 0 switches the histogram off
+__device__ __forceinline__ float2 hist_params(float kth, float smax) {
+  const bool ok = kth > -INFINITY && smax > kth && smax < INFINITY;
+  // the final k-th best usually lies below the sample's maximum, sometimes above it: cover twice that span
+  return ok ? make_float2(kth, 2.0f * (smax - kth) / (float)SM_HBINS) : make_float2(-INFINITY, 0.f);
+}
+
+__global__ void init_tau_kernel(float* tau, int32_t* qcount, int n, unsigned int* counters, unsigned int* hist,
+                                float2* hpar) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  for (int j = i; j < n; j += gridDim.x * blockDim.x) { tau[j] = -INFINITY; qcount[j] = 0; hpar[j] = make_float2(-INFINITY, 0.f); }
   if (i < 2 && counters) counters[i] = 0u;
+  for (int j = i; j < n * SM_HBINS; j += gridDim.x * blockDim.x) hist[j] = 0u;
 }
 
 // tau[q] = k-th best score of the sample pass (a valid lower bound on the final k-th best)
 __global__ void seed_tau_kernel(float* tau, int32_t* qcount, const float* __restrict__ sample_s,
-                                const int64_t* __restrict__ sample_i, int B, int n_pad, int k) {
+                                const int64_t* __restrict__ sample_i, int B, int n_pad, int k, float2* hpar) {
   int q = blockIdx.x * blockDim.x + threadIdx.x;
   if (q < n_pad) qcount[q] = 0;
-  if (q < B && sample_i[(int64_t)q * k + (k - 1)] >= 0) tau[q] = sample_s[(int64_t)q * k + (k - 1)];
+  if (q < B && sample_i[(int64_t)q * k + (k - 1)] >= 0) {
+    tau[q] = sample_s[(int64_t)q * k + (k - 1)];
+    hpar[q] = hist_params(sample_s[(int64_t)q * k + (k - 1)], sample_s[(int64_t)q * k]);
+  }
 }
 
 // Grid-barrier wait of the fused launch (all CTAs are co-resident: cooperative launch).  Bounded like the mbarrier
@@ -208,23 +232,28 @@ __device__ __forceinline__ void grid_wait(const unsigned int* counter, unsigned 
 // k-th largest of n floats in global memory (fused sample phase), computed by the 128 epilogue threads of a
 // CTA (named barrier 2): keys staged in `smem_f` (n <= SM_CAP * SM_MQ), MSD radix select over the
 // order-preserving 32-bit keys, 8 bits per round.  Returns -inf when fewer than k finite values exist.
-__device__ __forceinline__ float kth_largest_128(float* smem_f, const float* __restrict__ src, int n, int k, int tid) {
+__device__ __forceinline__ float kth_largest_128(float* smem_f, const float* __restrict__ src, int n, int k, int tid,
+                                                 float& vmax) {
   __shared__ uint32_t hist[256];
   __shared__ uint32_t s_prefix, s_rem;
   uint32_t* keys = reinterpret_cast<uint32_t*>(smem_f);
   int finite = 0;
+  uint32_t kmax = 0u;
   for (int i = tid; i < n; i += SM_MQ) {
     const float v = __ldcg(src + i);
     keys[i] = f2key(v);
+    kmax = max(kmax, keys[i]);
     finite += v > -INFINITY ? 1 : 0;
   }
   if (tid == 0) { s_prefix = 0u; s_rem = (uint32_t)k; }
-  // count finite values across the 128 threads through the histogram array
+  // count finite values across the 128 threads through the histogram array (hist[1]: the largest key)
   if (tid < 256 / 2) { hist[tid] = 0u; hist[tid + 128] = 0u; }
   ptx::named_bar_sync(2, SM_MQ);
   atomicAdd(&hist[0], (uint32_t)finite);
+  atomicMax(&hist[1], kmax);
   ptx::named_bar_sync(2, SM_MQ);
   const bool enough = hist[0] >= (uint32_t)k;
+  vmax = key2f(hist[1]);
   ptx::named_bar_sync(2, SM_MQ);
   if (!enough) return -INFINITY;
   for (int shift = 24; shift >= 0; shift -= 8) {
@@ -295,6 +324,8 @@ struct FusedArgs {
   float* samp;              // [128][n_slices * SM_SAMPLE_TOP] sample scores
   unsigned int* counters;   // two grid-barrier counters, zeroed before the launch
   int sample_tiles;         // tiles per CTA in the sample phase
+  unsigned int* hist;       // [queries][SM_HBINS] survivor histogram of the main pass (all modes but the sample pass), or NULL
+  float2* hpar;             // [queries] (lower edge of bin 0, bin width) — written by whoever seeds the bounds
 };
 
 // PAIR = true (query batches > 128): the two CTAs of a cluster own two adjacent 128-query tiles and the SAME document
@@ -316,6 +347,7 @@ scorer_body(const float* __restrict__ Q, const CUtensorMap& map_d, int B, int64_
   constexpr bool FUSED = MODE == 2;
   constexpr int ND_T = PAIR ? 2 * SM_ND : SM_ND;       // documents per (pair-)tile == accumulator columns per buffer
   constexpr int HALVES = PAIR ? 2 : 1;                 // 32-column accumulator halves the epilogue reads per tile
+  constexpr int SM_NACC = PAIR ? 4 : SM_NACC_MAX;      // accumulator buffers: 256 TMEM columns either way
   const uint32_t cta_rank = PAIR ? ptx::cluster_ctarank() : 0u;
   const bool leader = cta_rank == 0u;
   // which 32 documents of a 64-document pair tile this CTA loads: B rows [0, 32) come from rank 0's shared memory,
@@ -335,8 +367,8 @@ scorer_body(const float* __restrict__ Q, const CUtensorMap& map_d, int B, int64_
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(list_i) + SM_LISTI_BYTES);
   uint64_t* empty_bar = full_bar + SM_STAGES;
   uint64_t* acc_full = empty_bar + SM_STAGES;
-  uint64_t* acc_empty = acc_full + SM_NACC;
-  uint64_t* peer_full = acc_empty + SM_NACC;       // pair, leader only: "the peer's half of stage s has landed"
+  uint64_t* acc_empty = acc_full + SM_NACC_MAX;
+  uint64_t* peer_full = acc_empty + SM_NACC_MAX;       // pair, leader only: "the peer's half of stage s has landed"
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(peer_full + SM_STAGES);
   __shared__ uint64_t probe_bar;             // dbg & 64: the MMA warp waits for its own commit (timing experiment)
   // Screening (default; debug bit 29 switches it off).  The epilogue used to be ONE warp per scheduler doing everything
@@ -348,11 +380,14 @@ scorer_body(const float* __restrict__ Q, const CUtensorMap& map_d, int B, int64_
   // quarter's "keeper" warp (4-7), which owns the candidate lists and runs the unchanged filter / compaction code on
   // them, in tile order.  Thresholds flow keeper -> screener through `thr_sh` (stale = looser = safe).
   __shared__ float thr_sh[SM_MQ];            // per query: a score below this cannot enter the list
-  __shared__ int hit_q[4][8];                // per lane quarter: tiles the keeper must process (<= SM_NACC pending)
+  __shared__ int hit_q[4][16];               // per lane quarter: tiles the keeper must process (<= SM_NACC pending)
   __shared__ int hit_wr[4];                  // entries written to hit_q
   __shared__ int scr_tiles[4];               // tiles the screener has classified
   __shared__ int go_main[4];                 // fused launch: the keeper has published the seeded bounds
+  __shared__ float tgl_sh[SM_MQ];            // per query: the bound warps 2-3 read off the global survivor histogram / tau_g
+  __shared__ int keepers_done;               // keeper warps that have published their lists (the sweepers' exit signal)
   const bool screen_on = !(dbg & (1 << 29));
+  const bool hist_on = screen_on && MODE != 1 && fa.hist != nullptr && dbg >= 0;      // debug bit 31: histogram bound off
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 #define SM_MARK(slot)                                                                                   \
@@ -385,7 +420,9 @@ scorer_body(const float* __restrict__ Q, const CUtensorMap& map_d, int B, int64_
     ptx::mbar_init(&probe_bar, 1);
     ptx::fence_mbar_init();
     for (int w = 0; w < 4; ++w) { hit_wr[w] = 0; scr_tiles[w] = 0; go_main[w] = 0; }
+    keepers_done = 0;
   }
+  if (threadIdx.x < SM_MQ) tgl_sh[threadIdx.x] = -INFINITY;
   if (warp == 2) {
     if (PAIR) { ptx::tmem_alloc_2cta(tmem_slot, SM_TMEM_COLS); ptx::tmem_relinquish_2cta(); }
     else { ptx::tmem_alloc(tmem_slot, SM_TMEM_COLS); ptx::tmem_relinquish(); }
@@ -520,6 +557,51 @@ scorer_body(const float* __restrict__ Q, const CUtensorMap& map_d, int B, int64_
       if (ptx::elect_one()) ptx::mbar_arrive_cluster(ptx::mapa(ptx::smem_u32(peer_full + s), 0u));
       __syncwarp();
     }
+  } else if ((warp == 2 || warp == 3) && hist_on) {
+    // ===== bound sweepers: the two otherwise idle warps turn the global survivor histogram into per-query bounds =====
+    // Warp w sweeps queries [64 (w - 2), +64), four at a time: lane l reads bins 2l, 2l + 1 of a query (one coalesced
+    // 256-byte row), a suffix sum over the lanes gives the number of counted documents at or above every bin edge, and
+    // the highest edge with >= k of them — or tau_g, whichever is larger — goes to tgl_sh for the keepers and screeners.
+    volatile int* go_v = go_main;
+    volatile int* done_v = &keepers_done;
+    volatile float* tgl_v = tgl_sh;
+    if (FUSED) {
+      for (unsigned spin = 0; go_v[0] == 0 && *done_v < 4; ++spin) {
+        __nanosleep(256);
+        if (spin > (1u << 24)) __trap();
+      }
+    }
+    const int qb0 = 64 * (warp - 2);
+    bool stop = false;
+    while (!stop) {
+#pragma unroll 1
+      for (int g = 0; g < 64 && !stop; g += 4) {
+        uint2 c[4];
+        float2 hp[4];
+        float tq[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int q = q0 + qb0 + g + u;                    // < n_qt * 128: the scratch is padded to whole query tiles
+          c[u] = __ldcg(reinterpret_cast<const uint2*>(fa.hist + (size_t)q * SM_HBINS) + lane);
+          hp[u] = __ldcg(fa.hpar + q);
+          tq[u] = __ldcg(tau_g + q);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          uint32_t suf = c[u].x + c[u].y;                    // documents counted in this lane's two bins ...
+#pragma unroll
+          for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t v = __shfl_down_sync(0xffffffffu, suf, d);
+            if (lane + d < 32) suf += v;                     // ... and in all higher bins
+          }
+          const int cand = (suf - c[u].x >= (uint32_t)k) ? 2 * lane + 1 : (suf >= (uint32_t)k ? 2 * lane : -1);
+          const int best = __reduce_max_sync(0xffffffffu, cand);
+          const float bound = (best >= 0 && hp[u].y > 0.f) ? fmaf((float)best, hp[u].y, hp[u].x) : -INFINITY;
+          if (lane == 0) tgl_v[qb0 + g + u] = fmaxf(bound, tq[u]);
+        }
+        stop = *done_v >= 4;
+      }
+    }
   } else if (warp >= 8) {
     // ===== screener: one thread per query; classifies every tile, releases the ones without a survivor =====
     const int qw = warp - 8;
@@ -609,6 +691,7 @@ scorer_body(const float* __restrict__ Q, const CUtensorMap& map_d, int B, int64_
           ci = up ? ti : ci;
         }
       }
+      if (!smp) tgp = fmaxf(tgp, *(volatile float*)(tgl_sh + ql));
       const float thr = fmaxf(thr_v[ql], tgp);
       // the keeper masks the zero-filled rows of the last tile, so it always gets that tile
       const bool hit = !smp && (__any_sync(0xffffffffu, mx >= thr) || tail);
@@ -621,7 +704,7 @@ scorer_body(const float* __restrict__ Q, const CUtensorMap& map_d, int B, int64_
         }
       } else {
         if (lane == 0) {
-          hit_q[qw][wr & 7] = it;
+          hit_q[qw][wr & 15] = it;
           __threadfence_block();
           hit_wr_v[qw] = wr + 1;
         }
@@ -662,6 +745,16 @@ scorer_body(const float* __restrict__ Q, const CUtensorMap& map_d, int B, int64_
     // microseconds, so it is refreshed every 8 tiles and consumed one refresh later.
     float tg = (q_valid && !FUSED) ? __ldcg(tau_g + q) : (q_valid ? -INFINITY : INFINITY);   // seeded by the sample pass (or -inf)
     float tg_pending = tg;
+    // survivor histogram of this thread's query: lower edge of bin 0, bin width (0 = off), 1 / width
+    float h_lo = 0.f, h_w = 0.f, h_iw = 0.f;
+    unsigned int* h_row = hist_on ? fa.hist + (size_t)q * SM_HBINS : nullptr;
+    auto load_hist_params = [&]() {
+      if (hist_on && q_valid) {
+        const float2 hp = __ldcg(fa.hpar + q);
+        h_lo = hp.x; h_w = hp.y; h_iw = hp.y > 0.f ? 1.0f / hp.y : 0.f;
+      }
+    };
+    if (!FUSED) load_hist_params();
     // one tile of the epilogue; `smp` (compile-time) selects the register top-4 path of the sample phase.  Two
     // instantiations instead of a runtime flag: with the flag in the loop the main pass ran 10 % slower.
     // Filter one 32-score accumulator half: documents d0 .. d0 + 31, list ids lid0 + j.
@@ -728,6 +821,13 @@ scorer_body(const float* __restrict__ Q, const CUtensorMap& map_d, int B, int64_
           ls[cnt * SM_MQ] = scj;
           li[cnt * SM_MQ] = (uint16_t)(lid0 + j);
           ++cnt;
+          if (h_w > 0.f) {
+            // bin b holds scores >= fmaf(b, w, lo) — the very expression the sweepers evaluate, so rounding in the
+            // index arithmetic can only put a document one bin too LOW (a looser, still valid bound)
+            int b = min(max((int)((scj - h_lo) * h_iw), 0), SM_HBINS - 1);
+            if (scj < fmaf((float)b, h_w, h_lo)) --b;
+            if (b >= 0) atomicAdd(h_row + b, 1u);
+          }
         }
       }
       if (!smp && __any_sync(0xffffffffu, cnt > SM_CAP - SM_ND)) {
@@ -744,7 +844,7 @@ scorer_body(const float* __restrict__ Q, const CUtensorMap& map_d, int B, int64_
       const int buf = it % SM_NACC;
       const uint32_t aph = (uint32_t)(it / SM_NACC) & 1u;
       if ((screen_on || (it & 7) == 0) && q_valid && !smp) {
-        tg = fmaxf(tg, tg_pending);
+        tg = fmaxf(fmaxf(tg, tg_pending), *(volatile float*)(tgl_sh + ql));
         tg_pending = __ldcg(tau_g + q);
       }
       ptx::mbar_wait(acc_full + buf, aph);
@@ -797,7 +897,7 @@ scorer_body(const float* __restrict__ Q, const CUtensorMap& map_d, int B, int64_
       __syncwarp();
       if (__any_sync(0xffffffffu, cnt > SM_KEEP)) cnt = thread_compact(ls, li, cnt, k, tau, strict);
       if (q_valid) {
-        const float tgf = __ldcg(tau_g + q);
+        const float tgf = fmaxf(__ldcg(tau_g + q), *(volatile float*)(tgl_sh + ql));
         int n_keep = 0;
         for (int e = 0; e < SM_KEEP; ++e) n_keep += (e < cnt && ls[e * SM_MQ] >= tgf) ? 1 : 0;
         size_t ob = (size_t)q * (size_t)cap + (size_t)atomicAdd(out_n + q, n_keep);
@@ -825,7 +925,7 @@ scorer_body(const float* __restrict__ Q, const CUtensorMap& map_d, int B, int64_
     auto drain = [&](const int end, auto smp_tag) {
       for (unsigned spin = 0;;) {
         if (rd < hit_wr_v[qw]) {
-          const int it2 = *(volatile int*)&hit_q[qw][rd & 7];
+          const int it2 = *(volatile int*)&hit_q[qw][rd & 15];
           ++rd;
           if (decltype(smp_tag)::value) tile_body(it2, std::true_type{});
           else main_tile(it2);
@@ -856,9 +956,13 @@ scorer_body(const float* __restrict__ Q, const CUtensorMap& map_d, int B, int64_
       ptx::named_bar_sync(2, SM_MQ);
       // CTA c selects the bounds of queries c, c + n_ctas, ... (one query per CTA when B <= #CTAs)
       for (int qq = slice * (int)gridDim.x + qt; qq < B; qq += (int)n_ctas) {
+        float smax;
         const float kth = kth_largest_128(list_s, fa.samp + (size_t)qq * n_slices * SM_SAMPLE_TOP,
-                                          n_slices * SM_SAMPLE_TOP, k, ql);
-        if (ql == 0) tau_g[qq] = kth;
+                                          n_slices * SM_SAMPLE_TOP, k, ql, smax);
+        if (ql == 0) {
+          tau_g[qq] = kth;
+          if (fa.hpar) fa.hpar[qq] = hist_params(kth, smax);
+        }
         ptx::named_bar_sync(2, SM_MQ);
       }
       __threadfence();
@@ -871,6 +975,7 @@ scorer_body(const float* __restrict__ Q, const CUtensorMap& map_d, int B, int64_
       ptx::named_bar_sync(2, SM_MQ);
       tg = q_valid ? __ldcg(tau_g + q) : INFINITY;
       tg_pending = tg;
+      load_hist_params();
       if (screen_on) {
         *(volatile float*)(thr_sh + ql) = tg;
         __threadfence_block();
@@ -911,6 +1016,8 @@ scorer_body(const float* __restrict__ Q, const CUtensorMap& map_d, int B, int64_
     } else {
       publish();
     }
+    __syncwarp();
+    if (lane == 0) atomicAdd(&keepers_done, 1);          // the sweepers (warps 2-3) leave their loop at 4
   }
 
   if (threadIdx.x == 128) SM_MARK(3);        // candidates published
@@ -1133,7 +1240,7 @@ struct MmaPlan {
   bool pair;                        // CTA pairs (cta_group::2, 64-document tiles): every batch of more than one query tile
   int nd_t;                         // documents per tile: 32, pair 64
   int seg_tiles, n_segs, cap;       // id-segment length (tiles), segments per CTA, candidate slots per query
-  int64_t tau_off, outs_off, outi_off, outn_off, samp_off, cnt_off, total;
+  int64_t tau_off, outs_off, outi_off, outn_off, samp_off, cnt_off, hist_off, hpar_off, total;
 };
 
 MmaPlan mma_plan(int B, int64_t N) {
@@ -1159,7 +1266,9 @@ MmaPlan mma_plan(int B, int64_t N) {
   p.outn_off = align(p.outi_off + bp * p.cap * 4);
   p.samp_off = align(p.outn_off + bp * 4);                                   // fused mode: [queries][n_slices][4] fp32
   p.cnt_off = align(p.samp_off + bp * p.n_slices * SM_SAMPLE_TOP * 4);
-  p.total = align(p.cnt_off + 16);
+  p.hist_off = align(p.cnt_off + 16);                                        // [queries][SM_HBINS] u32
+  p.hpar_off = align(p.hist_off + bp * SM_HBINS * 4);                        // [queries] float2
+  p.total = align(p.hpar_off + bp * 8);
   return p;
 }
 
@@ -1203,9 +1312,11 @@ int launch_score_topk_mma(const float* Q, int B, const float* docs, int64_t N, i
   const int nq_pad = p.n_qt * SM_MQ;
   float* samp = reinterpret_cast<float*>(ws + p.samp_off);
   unsigned int* counters = reinterpret_cast<unsigned int*>(ws + p.cnt_off);
-  init_tau_kernel<<<ceil_div(nq_pad, 256), 256, 0, st>>>(tau, outn, nq_pad, counters);
+  unsigned int* hist = reinterpret_cast<unsigned int*>(ws + p.hist_off);
+  float2* hpar = reinterpret_cast<float2*>(ws + p.hpar_off);
+  init_tau_kernel<<<std::min(ceil_div(nq_pad * SM_HBINS, 256), 2 * sm_count()), 256, 0, st>>>(tau, outn, nq_pad, counters, hist, hpar);
   TTR_CHECK_LAUNCH();
-  const size_t smem = (size_t)SM_STAGES * SM_STAGE_BYTES + SM_LIST_BYTES + SM_LISTI_BYTES + (3 * SM_STAGES + 2 * SM_NACC) * 8 + 16 + 1024;
+  const size_t smem = (size_t)SM_STAGES * SM_STAGE_BYTES + SM_LIST_BYTES + SM_LISTI_BYTES + (3 * SM_STAGES + 2 * SM_NACC_MAX) * 8 + 16 + 1024;
   static thread_local int attr_dev = -1;
   int cur_dev = 0;
   TTR_CHECK_CUDA(cudaGetDevice(&cur_dev));
@@ -1217,7 +1328,7 @@ int launch_score_topk_mma(const float* Q, int B, const float* docs, int64_t N, i
     }
     attr_dev = cur_dev;
   }
-  FusedArgs fa{nullptr, nullptr, 0};
+  FusedArgs fa{nullptr, nullptr, 0, hist, hpar};
   long long* tr = nullptr;
   int dbgv = g_debug_flags;
   CUtensorMap map;
@@ -1252,7 +1363,7 @@ int launch_score_topk_mma(const float* Q, int B, const float* docs, int64_t N, i
     int rcf = make_tf32_rowmajor_map(&map, docs, N, SM_DIM, SM_ND);
     if (rcf != TTR_OK) return rcf;
     // every query sees the same number of sample documents whatever the slice count
-    fa = FusedArgs{samp, counters, (int)ceil_div64(n_sample / p.nd_t, (int64_t)p.n_slices)};
+    fa = FusedArgs{samp, counters, (int)ceil_div64(n_sample / p.nd_t, (int64_t)p.n_slices), hist, hpar};
     tr = g_score_trace;
     cudaError_t ce = launch_scorer(scorer_fn<2>(p.pair), dim3(p.n_qt, p.n_slices), smem, st, p.pair, true, args);
     if (ce == cudaSuccess) {
@@ -1261,7 +1372,7 @@ int launch_score_topk_mma(const float* Q, int B, const float* docs, int64_t N, i
     }
     (void)cudaGetLastError();                 // not co-resident on this device/partition: use the two-pass path
     fused_ok[cur_dev & 63][p.pair] = -1;
-    fa = FusedArgs{nullptr, nullptr, 0};
+    fa = FusedArgs{nullptr, nullptr, 0, hist, hpar};
     tr = nullptr;
   }
   if (N >= 16 * n_sample && sample_useful && !(g_debug_flags & 256)) {
@@ -1272,7 +1383,7 @@ int launch_score_topk_mma(const float* Q, int B, const float* docs, int64_t N, i
     TTR_CHECK_CUDA(launch_scorer(scorer_fn<1>(ps.pair), dim3(ps.n_qt, ps.n_slices), smem, st, ps.pair, false, args));
     rc = launch_select_merge(outs, outi, outn, B, ps.cap, k, 0, out_scores, out_idx, st);
     if (rc != TTR_OK) return rc;
-    seed_tau_kernel<<<ceil_div(nq_pad, 256), 256, 0, st>>>(tau, outn, out_scores, out_idx, B, nq_pad, k);
+    seed_tau_kernel<<<ceil_div(nq_pad, 256), 256, 0, st>>>(tau, outn, out_scores, out_idx, B, nq_pad, k, hpar);
     TTR_CHECK_LAUNCH();
   }
   int rc = make_tf32_rowmajor_map(&map, docs, N, SM_DIM, SM_ND);

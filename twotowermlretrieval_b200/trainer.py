@@ -45,6 +45,13 @@ class TwoTowerTrainer:
         self.val_losses: List[float] = []
         self.best_val_loss = float("inf")
         self.log_fn = log_fn or (lambda d: None)
+        # The three tower passes of a step (query, positive, negative) are independent until the loss.  Each is a chain
+        # of latency-bound recurrence kernels that leave SMs, issue slots and HBM idle, so they run on three streams:
+        # one tower's projection / weight-gradient GEMMs fill the gaps of another tower's recurrence.  autograd runs
+        # every backward node on the stream of its forward, so the backward passes overlap the same way.
+        # 1 = one stream (everything in program order).
+        self.tower_streams = int(config.get("TOWER_STREAMS", 3))
+        self._lanes: List[torch.cuda.Stream] = []
 
     # ------------------------------------------------------------------ metrics
     def compute_batch_metrics(self, q_vec, pos_vec, neg_vec) -> Dict[str, float]:
@@ -78,13 +85,39 @@ class TwoTowerTrainer:
         pos_batch = pos_batch.to(self.device, non_blocking=True)
         neg_batch = neg_batch.to(self.device, non_blocking=True)
         self.optimizer.zero_grad()
-        q_vec = self.model.encode_query(query_batch)
-        pos_vec = self.model.encode_document(pos_batch)
-        neg_vec = self.model.encode_document(neg_batch)
+        if self.tower_streams > 1 and query_batch.is_cuda:
+            q_vec, pos_vec, neg_vec = self._encode_on_lanes(query_batch, pos_batch, neg_batch)
+        else:
+            q_vec = self.model.encode_query(query_batch)
+            pos_vec = self.model.encode_document(pos_batch)
+            neg_vec = self.model.encode_document(neg_batch)
         loss = self.loss_function((q_vec, pos_vec, neg_vec))
         loss.backward()
         self.optimizer.step()
         return loss.detach(), q_vec.detach(), pos_vec.detach(), neg_vec.detach()
+
+    def _encode_on_lanes(self, query_batch, pos_batch, neg_batch):
+        dev = query_batch.device
+        main = torch.cuda.current_stream(dev)
+        n = min(self.tower_streams, 3)
+        if len(self._lanes) != n or self._lanes[0].device != dev:
+            self._lanes = [torch.cuda.Stream(device=dev) for _ in range(n)]
+        self.model._ensure_flat()                 # lazily rebuilt buffers must exist before the lanes fork
+        for s in self._lanes:
+            s.wait_stream(main)
+        outs = []
+        jobs = ((self.model.encode_query, query_batch), (self.model.encode_document, pos_batch),
+                (self.model.encode_document, neg_batch))
+        for i, (fn, ids) in enumerate(jobs):
+            s = self._lanes[i % n]
+            with torch.cuda.stream(s):
+                e = fn(ids)
+            ids.record_stream(s)
+            e.record_stream(main)
+            outs.append(e)
+        for s in self._lanes:
+            main.wait_stream(s)
+        return outs
 
     def train_epoch(self, train_loader, val_loader, epoch):
         self.model.train()
