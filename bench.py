@@ -766,9 +766,9 @@ def leg_encode(c, cpu_ok):
     with torch.no_grad():
         for b in batches:
             enc(b)
-        encode_padded_batches(enc, batches)
-        ms_c1 = c.timed(lambda s: [enc(b) for b in batches], 3)              # one batch at a time, one stream
-        ms_c = c.timed(lambda s: encode_padded_batches(enc, batches), 3)     # what encode_rows does: two compute lanes
+        encode_padded_batches(enc, batches, streams=2)
+        ms_c = c.timed(lambda s: encode_padded_batches(enc, batches), 3)              # one batch at a time (default)
+        ms_c2 = c.timed(lambda s: encode_padded_batches(enc, batches, streams=2), 3)  # A/B: two compute streams (slower)
     toks_c = int(l2.sum())
     # the projection GEMMs alone, same token count, own kernel time (north_star: >= 50 % tensor-pipe utilisation)
     proj = {}
@@ -796,9 +796,9 @@ def leg_encode(c, cpu_ok):
            "h2d_bytes": toks * 8, "path": "host (flat ids, lengths) -> encode_rows -> rows of the resident search shard",
            "compute_only": {"passages_per_s": NP * c.world / (ms_c * 1e-3), "tokens_per_s": toks_c * c.world / (ms_c * 1e-3),
                             "ms_per_61440_passages": ms_c, "whole_tower_tflops_per_gpu": toks_c * 3_760_128.0 / (ms_c * 1e-3) / 1e12,
-                            "one_lane": {"passages_per_s": NP * c.world / (ms_c1 * 1e-3), "ms_per_61440_passages": ms_c1},
-                            "note": "device-resident ids, pre-sorted 7,680-row batches, consecutive batches on two compute "
-                                    "streams (encode.encode_padded_batches); one_lane = one batch at a time"},
+                            "two_streams": {"passages_per_s": NP * c.world / (ms_c2 * 1e-3), "ms_per_61440_passages": ms_c2},
+                            "note": "device-resident ids, pre-sorted 7,680-row batches (encode.encode_padded_batches); "
+                                    "two_streams = consecutive batches on alternating compute streams (A/B, not the default)"},
            "roofline": {"bound": "tensor", "achieved": proj_tf, "peak": peak_bf16, "unit": "TFLOP/s", "frac": proj_tf / peak_bf16,
                         "traffic": None, "kernel": "gemm_bias_kernel<F16> (input projections, kind::f16), own kernel time on the "
                         "token count of the compute-only batches", "per_layer": proj, "peak_source": c.peak_src + " bf16 burst"},

@@ -232,10 +232,13 @@ __device__ __forceinline__ void grid_wait(const unsigned int* counter, unsigned 
 // k-th largest of n floats in global memory (fused sample phase), computed by the 128 epilogue threads of a
 // CTA (named barrier 2): keys staged in `smem_f` (n <= SM_CAP * SM_MQ), MSD radix select over the
 // order-preserving 32-bit keys, 8 bits per round.  Returns -inf when fewer than k finite values exist.
-__device__ __forceinline__ float kth_largest_128(float* smem_f, const float* __restrict__ src, int n, int k, int tid,
-                                                 float& vmax) {
-  __shared__ uint32_t hist[256];
-  __shared__ uint32_t s_prefix, s_rem;
+// `scratch`: 258 words of shared memory nobody else uses meanwhile (the caller passes the idle id lists — static shared
+// memory is down to its last few hundred bytes next to the 225 KB of ring + lists).
+__device__ __forceinline__ float kth_largest_128(float* smem_f, uint32_t* scratch, const float* __restrict__ src, int n,
+                                                 int k, int tid, float& vmax) {
+  uint32_t* hist = scratch;
+  uint32_t& s_prefix = scratch[256];
+  uint32_t& s_rem = scratch[257];
   uint32_t* keys = reinterpret_cast<uint32_t*>(smem_f);
   int finite = 0;
   uint32_t kmax = 0u;
@@ -957,8 +960,8 @@ scorer_body(const float* __restrict__ Q, const CUtensorMap& map_d, int B, int64_
       // CTA c selects the bounds of queries c, c + n_ctas, ... (one query per CTA when B <= #CTAs)
       for (int qq = slice * (int)gridDim.x + qt; qq < B; qq += (int)n_ctas) {
         float smax;
-        const float kth = kth_largest_128(list_s, fa.samp + (size_t)qq * n_slices * SM_SAMPLE_TOP,
-                                          n_slices * SM_SAMPLE_TOP, k, ql, smax);
+        const float kth = kth_largest_128(list_s, reinterpret_cast<uint32_t*>(list_i),
+                                          fa.samp + (size_t)qq * n_slices * SM_SAMPLE_TOP, n_slices * SM_SAMPLE_TOP, k, ql, smax);
         if (ql == 0) {
           tau_g[qq] = kth;
           if (fa.hpar) fa.hpar[qq] = hist_params(kth, smax);

@@ -9,10 +9,10 @@ copy engine moves batch i and the SMs encode batch i-1), encoded with the zero-l
 disabled (no device->host sync per batch), and written straight into the resident output
 matrix — e.g. a rank's shard of the search index — in caller order.
 
-Consecutive batches alternate between TWO compute streams.  The tcgen05 recurrence is a latency chain
-that holds 15 clusters of 8 CTAs (120 of the 148 SMs) and leaves most issue slots and the whole HBM
-stream idle; with a second batch in flight its gather, projection GEMMs and head run on the SMs and in
-the bubbles the first batch's recurrence leaves (and vice versa), instead of one kernel at a time.
+`streams` > 1 alternates consecutive batches between several compute streams.  Measured on a B200 (r2,
+`tools/encode_rows_profile.py`, 400 k passages) that is SLOWER — 0.98-1.18 M passages/s on one stream, 0.41-0.76 M
+on two, 0.41 M on three: the recurrence needs 8 free SMs of one GPC per cluster, and a second batch's one-CTA-per-SM
+GEMM / gather CTAs fragment exactly those — so the default stays one stream; the switch is kept for the A/B.
 """
 from __future__ import annotations
 
@@ -103,9 +103,9 @@ class _Lanes:
                 self.main.wait_stream(s)
 
 
-def encode_padded_batches(encoder, batches: Sequence[torch.Tensor], streams: int = 2) -> "list[torch.Tensor]":
-    """Encode device-resident padded id batches [R_i, T_i] (inference, zero-length check off) with consecutive
-    batches on alternating compute streams; returns the embeddings in order.  Results are ordered after the
+def encode_padded_batches(encoder, batches: Sequence[torch.Tensor], streams: int = 1) -> "list[torch.Tensor]":
+    """Encode device-resident padded id batches [R_i, T_i] (inference, zero-length check off), optionally with
+    consecutive batches on alternating compute streams; returns the embeddings in order.  Results are ordered after the
     caller's current stream like any other call."""
     if not batches:
         return []
@@ -131,7 +131,7 @@ def encode_padded_batches(encoder, batches: Sequence[torch.Tensor], streams: int
 
 
 def encode_rows(encoder, rows: Union[Ragged, Sequence[Sequence[int]]], device, out: Optional[torch.Tensor] = None,
-                out_offset: int = 0, max_tokens: int = 524288, max_rows: int = 15360, streams: int = 2) -> torch.Tensor:
+                out_offset: int = 0, max_tokens: int = 524288, max_rows: int = 15360, streams: int = 1) -> torch.Tensor:
     """Encode tokenised rows with `encoder` (an RNNEncoder) -> fp32 [n, H] on `device`
     (rows `out[out_offset : out_offset + n]` if `out` is given).  `rows` is a list of id lists or a
     (flat ids, lengths) pair.  Raises RuntimeError for empty rows like the reference's

@@ -102,6 +102,11 @@ class TwoTowerTrainer:
         n = min(self.tower_streams, 3)
         if len(self._lanes) != n or self._lanes[0].device != dev:
             self._lanes = [torch.cuda.Stream(device=dev) for _ in range(n)]
+            # the parameters' AccumulateGrad nodes live on the stream the model was built on; gradients now arrive from
+            # the lanes, which autograd synchronises correctly but reports on every backward
+            quiet = getattr(torch.autograd.graph, "set_warn_on_accumulate_grad_stream_mismatch", None)
+            if quiet is not None:
+                quiet(False)
         self.model._ensure_flat()                 # lazily rebuilt buffers must exist before the lanes fork
         for s in self._lanes:
             s.wait_stream(main)
