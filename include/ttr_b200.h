@@ -169,6 +169,12 @@ int ttr_positive_rank(const float* Q, const float* docs, const int64_t* target, 
  * a caller-owned (pinned) buffer; output row r = ragged row rows[r] (flat ids, start offsets, lengths). */
 int ttr_pack_padded_i64(const int64_t* flat, const int64_t* starts, const int64_t* lengths,
                         const int64_t* rows, int64_t n_rows, int64_t T, int64_t* out);
+/* The same, also returning the number of non-zero ids copied (the packed token count the device plan will find:
+ * backend/model.py:52, `lengths = (x != 0).sum(1)`) and the number of rows without any (for which the reference's
+ * pack_padded_sequence raises, model.py:57). */
+int ttr_pack_padded_count_i64(const int64_t* flat, const int64_t* starts, const int64_t* lengths,
+                              const int64_t* rows, int64_t n_rows, int64_t T, int64_t* out,
+                              int64_t* nnz_total, int64_t* zero_rows);
 /* Test/debug switches: bit0 = force the generic (any-H) GRU kernels, bit1 = encode TMA maps
  * as FLOAT32 instead of TFLOAT32 (hardware truncation instead of round-to-nearest),
  * bit2 = force the CUDA-core streaming scorer for every batch size, bit8 = no sample pass,

@@ -273,6 +273,19 @@ def test_host_packer_matches_pad_sequence():
     ref = torch.nn.utils.rnn.pad_sequence([torch.tensor(flat[starts[r]:starts[r] + lengths[r]]) for r in rows],
                                           batch_first=True, padding_value=0)
     assert torch.equal(out, ref)
+    # the counting variant: same matrix + number of non-zero ids + number of rows without any
+    import ctypes
+    flat2 = flat.copy()
+    flat2[starts[rows[3]]:starts[rows[3]] + lengths[rows[3]]] = 0          # an all-zero row
+    flat2[starts[rows[5]] + 1] = 0                                         # a zero in the middle of a row
+    out2 = torch.full((64, T), -1, dtype=torch.int64)
+    nnz, zero = ctypes.c_int64(-1), ctypes.c_int64(-1)
+    _lib.call_nostream("ttr_pack_padded_count_i64", flat2.ctypes.data, starts.ctypes.data, lengths.ctypes.data,
+                       rows.ctypes.data, 64, T, out2.data_ptr(), ctypes.addressof(nnz), ctypes.addressof(zero))
+    ref2 = torch.nn.utils.rnn.pad_sequence([torch.tensor(flat2[starts[r]:starts[r] + lengths[r]]) for r in rows],
+                                           batch_first=True, padding_value=0)
+    assert torch.equal(out2, ref2)
+    assert nnz.value == int((ref2 != 0).sum()) and zero.value == 1
 
 
 def test_plan_batches_rounds_rows_to_whole_recurrence_waves():

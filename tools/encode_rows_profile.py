@@ -18,13 +18,13 @@ flat, lens = synth.make_ragged_tokens(n, "passage", cfg["VOCAB_SIZE"], seed=2)
 out = torch.empty(n, 256, device=dev)
 encode_rows(enc, (flat[: int(lens[:4096].sum())], lens[:4096]), dev, out=out)
 torch.cuda.synchronize()
-for lanes in (1, 2, 1):
+for lanes, max_tokens, max_rows in ((1, 524288, 15360), (1, 1048576, 15360), (1, 1048576, 30720), (1, 262144, 7680), (1, 524288, 15360)):
     smp = bench.ClockSampler(0); smp.start()
     t0 = time.perf_counter()
-    encode_rows(enc, (flat, lens), dev, out=out, streams=lanes)
+    encode_rows(enc, (flat, lens), dev, out=out, streams=lanes, max_tokens=max_tokens, max_rows=max_rows)
     t_host = time.perf_counter() - t0
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     clk = smp.stop()
-    print(f"lanes {lanes}: {n} passages {int(lens.sum())} tokens: {dt*1e3:.1f} ms ({t_host*1e3:.1f} ms until the host returned) -> "
-          f"{n/dt:,.0f} passages/s, {lens.sum()/dt/1e6:.1f} Mtok/s; clocks {clk}")
+    print(f"lanes {lanes} max_tokens {max_tokens} max_rows {max_rows}: {n} passages {int(lens.sum())} tokens: {dt*1e3:.1f} ms "
+          f"({t_host*1e3:.1f} ms until the host returned) -> {n/dt:,.0f} passages/s, {lens.sum()/dt/1e6:.1f} Mtok/s; clocks {clk}")

@@ -24,6 +24,7 @@ _SIGNATURES = {
     "ttr_debug_gru_tc_max_clusters": [P],
     "ttr_debug_set_trace": [P],
     "ttr_pack_padded_i64": [P, P, P, P, I64, I64, P],
+    "ttr_pack_padded_count_i64": [P, P, P, P, I64, I64, P, P, P],
     "ttr_seq_plan": [P, I32, I32, P, P, P, P, P],
     "ttr_embed_gather": [P, I32, I32, P, I64, I32, P, P, P, I32, P],
     "ttr_embed_scatter_grad": [P, I32, I32, I64, I32, P, P, P, P, P],

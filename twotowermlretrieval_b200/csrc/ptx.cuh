@@ -189,6 +189,11 @@ __device__ __forceinline__ void tmem_ld_wait() {
 // supplies its 128 rows of A (here: from its own tensor memory) and HALF of the B rows (N/2, from its own
 // shared memory at the same offset); each CTA's tensor memory receives its 128 x N block of D.  Only the
 // leader (rank 0) issues; completion is multicast to barriers at the same offset in both CTAs.
+__device__ __forceinline__ long long globaltimer_ns() {
+  long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));

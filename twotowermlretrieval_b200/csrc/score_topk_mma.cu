@@ -576,7 +576,13 @@ scorer_body(const float* __restrict__ Q, const CUtensorMap& map_d, int B, int64_
     }
     const int qb0 = 64 * (warp - 2);
     bool stop = false;
+    // The bound rises like the logarithm of the scanned fraction, so sweeps are spaced geometrically: the next one
+    // starts when the scan is 1/8 older (at least 2 us later).  Back-to-back sweeps of all CTAs were ~1 TB/s of L2
+    // reads for nothing on a full-corpus scan.
+    const long long t_start = ptx::globaltimer_ns();
     while (!stop) {
+      const long long t_now = ptx::globaltimer_ns();
+      const long long t_next = t_now + max(2000ll, (t_now - t_start) >> 3);
 #pragma unroll 1
       for (int g = 0; g < 64 && !stop; g += 4) {
         uint2 c[4];
@@ -602,6 +608,10 @@ scorer_body(const float* __restrict__ Q, const CUtensorMap& map_d, int B, int64_
           const float bound = (best >= 0 && hp[u].y > 0.f) ? fmaf((float)best, hp[u].y, hp[u].x) : -INFINITY;
           if (lane == 0) tgl_v[qb0 + g + u] = fmaxf(bound, tq[u]);
         }
+        stop = *done_v >= 4;
+      }
+      while (!stop && ptx::globaltimer_ns() < t_next) {
+        __nanosleep(500);
         stop = *done_v >= 4;
       }
     }

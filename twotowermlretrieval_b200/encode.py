@@ -33,7 +33,12 @@ def plan_batches(lengths: np.ndarray, max_tokens: int, max_rows: int, row_quantu
     """Greedy batches over rows sorted by length (descending): each batch holds at most
     `max_rows` rows and `max_tokens` padded tokens; row counts above `row_quantum` are rounded down to a
     multiple of it so the recurrence kernel runs whole waves of clusters.  Returns (order, [(lo, hi), ...])."""
-    order = np.argsort(-lengths, kind="stable")
+    mx = int(lengths.max()) if len(lengths) else 0
+    if 0 <= int(lengths.min() if len(lengths) else 0) and mx < 65536:
+        # 16-bit keys: numpy's stable sort is a radix sort there (19 ms instead of 127 ms per 1.1 M rows)
+        order = np.argsort((mx - lengths).astype(np.uint16), kind="stable")
+    else:
+        order = np.argsort(-lengths, kind="stable")
     sl = lengths[order]
     bounds, lo, n = [], 0, len(sl)
     while lo < n:
@@ -144,15 +149,17 @@ def encode_rows(encoder, rows: Union[Ragged, Sequence[Sequence[int]]], device, o
         out_offset = 0
     if n == 0:
         return out
+    from .model import _ZERO_LEN_MSG
     starts = np.zeros(n + 1, dtype=np.int64)
     np.cumsum(lengths, out=starts[1:])
-    # quirk #1: the effective length is the count of non-zero ids; rows are passed through untouched,
-    # the device plan recounts.  Only the all-zero / empty case is an error.
-    nnz = np.add.reduceat((flat != 0).astype(np.int64), starts[:-1][lengths > 0]) if flat.size else np.zeros(0, np.int64)
-    if (lengths <= 0).any() or (nnz <= 0).any():
-        from .model import _ZERO_LEN_MSG
+    # quirk #1: the effective length is the count of non-zero ids; rows are passed through untouched, the device
+    # plan recounts.  Only the all-zero / empty case is an error; the packer counts non-zero ids while it copies
+    # (no separate pass over the corpus before the first batch), so an all-zero row raises when its batch is packed.
+    if (lengths <= 0).any():
         raise RuntimeError(_ZERO_LEN_MSG)
     order, bounds = plan_batches(lengths, max_tokens, max_rows)
+    import ctypes
+    nnz_total, zero_rows = ctypes.c_int64(0), ctypes.c_int64(0)
     max_tok = max((hi - lo) * int(lengths[order[lo]]) for lo, hi in bounds)
     max_row = max(hi - lo for lo, hi in bounds)
     stage = [_Staging(max_tok, max_row) for _ in range(2)]
@@ -172,8 +179,11 @@ def encode_rows(encoder, rows: Union[Ragged, Sequence[Sequence[int]]], device, o
                 R, T = hi - lo, int(lengths[idx[0]])
                 # fill the padded [R, T] view of the pinned buffer from the ragged rows (host memcpy per row, in C)
                 idx = np.ascontiguousarray(idx, dtype=np.int64)
-                _lib.call_nostream("ttr_pack_padded_i64", flat.ctypes.data, starts.ctypes.data, lengths.ctypes.data,
-                                   idx.ctypes.data, R, T, st.ids.data_ptr())
+                _lib.call_nostream("ttr_pack_padded_count_i64", flat.ctypes.data, starts.ctypes.data, lengths.ctypes.data,
+                                   idx.ctypes.data, R, T, st.ids.data_ptr(), ctypes.addressof(nnz_total),
+                                   ctypes.addressof(zero_rows))
+                if zero_rows.value:
+                    raise RuntimeError(_ZERO_LEN_MSG)
                 st.idx_np[:R] = idx + out_offset
                 with torch.cuda.stream(copy_stream):
                     dev_ids = st.ids[:R * T].view(R, T).to(dev, non_blocking=True)
@@ -182,7 +192,7 @@ def encode_rows(encoder, rows: Union[Ragged, Sequence[Sequence[int]]], device, o
                     st.copied.record(copy_stream)
                 cs = lanes.next()
                 cs.wait_stream(copy_stream)
-                encoder._token_bound = int(nnz[idx].sum())      # rows of the packed per-token matrices (<= R * T)
+                encoder._token_bound = int(nnz_total.value)     # rows of the packed per-token matrices (<= R * T)
                 with torch.cuda.stream(cs):
                     emb = encoder(dev_ids)
                     out.index_copy_(0, dev_idx, emb)            # distinct rows per batch: lanes never write the same row
