@@ -1341,6 +1341,13 @@ int launch_score_topk_mma(const float* Q, int B, const float* docs, int64_t N, i
     }
     attr_dev = cur_dev;
   }
+  // The survivor histogram pays where a CTA's own lists cannot tighten the bound fast enough: short scans (<= 640 tiles
+  // per CTA: 1/4 of the corpus and less at B <= 128) and CTA pairs (64-document tiles, twice the survivors per tile).
+  // Same-box A/B (r2): N = 1.1 M, B = 128: 0.248 -> 0.225 ms; N = 1 M, B = 256: 0.375 -> 0.256 ms; N = 8.84 M, B = 256:
+  // 2.05 -> 1.85 ms; but N = 8.84 M, B = 128 (1,867 tiles per CTA, lists fill by themselves): 1.326 -> 1.381 ms, so off there.
+  const int64_t scan_tiles_per_cta = ceil_div64(ceil_div64(N, (int64_t)p.nd_t), (int64_t)p.n_slices);
+  const bool use_hist = p.pair || scan_tiles_per_cta <= 640;
+  if (!use_hist) hist = nullptr;
   FusedArgs fa{nullptr, nullptr, 0, hist, hpar};
   long long* tr = nullptr;
   int dbgv = g_debug_flags;

@@ -136,9 +136,11 @@ def encode_padded_batches(encoder, batches: Sequence[torch.Tensor], streams: int
 
 
 def encode_rows(encoder, rows: Union[Ragged, Sequence[Sequence[int]]], device, out: Optional[torch.Tensor] = None,
-                out_offset: int = 0, max_tokens: int = 524288, max_rows: int = 15360, streams: int = 1) -> torch.Tensor:
+                out_offset: int = 0, max_tokens: int = 1048576, max_rows: int = 30720, streams: int = 1) -> torch.Tensor:
     """Encode tokenised rows with `encoder` (an RNNEncoder) -> fp32 [n, H] on `device`
-    (rows `out[out_offset : out_offset + n]` if `out` is given).  `rows` is a list of id lists or a
+    (rows `out[out_offset : out_offset + n]` if `out` is given).  Batches hold up to `max_tokens` padded tokens /
+    `max_rows` rows (r2, 600 k passages end to end: 1.59 M passages/s at 524,288 / 15,360, 1.76 M at 1,048,576 /
+    30,720 — eight waves of the recurrence per launch instead of four; ~5 GB of fp16 gi / y / X in flight).  `rows` is a list of id lists or a
     (flat ids, lengths) pair.  Raises RuntimeError for empty rows like the reference's
     pack_padded_sequence (quirk #2)."""
     flat, lengths = to_ragged(rows)
