@@ -358,11 +358,54 @@ __device__ __forceinline__ void f16_half_to_stage(uint32_t tmem_col0, int q, int
 // bound by the ring, not by MMAs or HBM: 5 stages x 32 KB in flight against ~3.5 k cycles of load latency is one
 // 256 x 256 x 64 k-block per ~800 cycles, while its 4 (3.25 real) k-steps need 512; resident W halves the bytes per
 // k-block and leaves room for 7 stages -> 3.5x the k-blocks in flight.
+// 64 columns already in registers (two 32-column tcgen05.ld results) + bias -> row-major fp16 staging (GP_PITCH)
+__device__ __forceinline__ void f16_regs_to_stage(const uint32_t (&ra)[32], const uint32_t (&rb)[32], int r_in_tile,
+                                                  unsigned char* my_stage, const float* __restrict__ bias_sm) {
+#pragma unroll
+  for (int c = 0; c < 2; ++c) {
+    const uint32_t (&cur)[32] = c ? rb : ra;
+    uint4* row = reinterpret_cast<uint4*>(my_stage + r_in_tile * GP_PITCH + c * 64);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {                   // four 16-byte chunks = 32 halves
+      const float4 b0 = *reinterpret_cast<const float4*>(bias_sm + 32 * c + 8 * j);
+      const float4 b1 = *reinterpret_cast<const float4*>(bias_sm + 32 * c + 8 * j + 4);
+      const __half2 h0 = __floats2half2_rn(__uint_as_float(cur[8 * j + 0]) + b0.x, __uint_as_float(cur[8 * j + 1]) + b0.y);
+      const __half2 h1 = __floats2half2_rn(__uint_as_float(cur[8 * j + 2]) + b0.z, __uint_as_float(cur[8 * j + 3]) + b0.w);
+      const __half2 h2 = __floats2half2_rn(__uint_as_float(cur[8 * j + 4]) + b1.x, __uint_as_float(cur[8 * j + 5]) + b1.y);
+      const __half2 h3 = __floats2half2_rn(__uint_as_float(cur[8 * j + 6]) + b1.z, __uint_as_float(cur[8 * j + 7]) + b1.w);
+      row[j] = make_uint4(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1),
+                          *reinterpret_cast<const uint32_t*>(&h2), *reinterpret_cast<const uint32_t*>(&h3));
+    }
+  }
+}
+
+// the same into a dense [128 rows][128 B] staging tile in the SWIZZLE_128B pattern of the output tensor map (16-byte
+// chunk index XOR row mod 8): the source of a TMA store
+__device__ __forceinline__ void f16_regs_to_swizzled(const uint32_t (&ra)[32], const uint32_t (&rb)[32], int r_in_tile,
+                                                     unsigned char* my_stage, const float* __restrict__ bias_sm) {
+  uint4* row = reinterpret_cast<uint4*>(my_stage + r_in_tile * 128);
+#pragma unroll
+  for (int c = 0; c < 2; ++c) {
+    const uint32_t (&cur)[32] = c ? rb : ra;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float4 b0 = *reinterpret_cast<const float4*>(bias_sm + 32 * c + 8 * j);
+      const float4 b1 = *reinterpret_cast<const float4*>(bias_sm + 32 * c + 8 * j + 4);
+      const __half2 h0 = __floats2half2_rn(__uint_as_float(cur[8 * j + 0]) + b0.x, __uint_as_float(cur[8 * j + 1]) + b0.y);
+      const __half2 h1 = __floats2half2_rn(__uint_as_float(cur[8 * j + 2]) + b0.z, __uint_as_float(cur[8 * j + 3]) + b0.w);
+      const __half2 h2 = __floats2half2_rn(__uint_as_float(cur[8 * j + 4]) + b1.x, __uint_as_float(cur[8 * j + 5]) + b1.y);
+      const __half2 h3 = __floats2half2_rn(__uint_as_float(cur[8 * j + 6]) + b1.z, __uint_as_float(cur[8 * j + 7]) + b1.w);
+      row[(4 * c + j) ^ (r_in_tile & 7)] = make_uint4(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1),
+                                                      *reinterpret_cast<const uint32_t*>(&h2), *reinterpret_cast<const uint32_t*>(&h3));
+    }
+  }
+}
+
 template <bool WRES>
 __global__ void __launch_bounds__(G_THREADS, 1)
 gemm_bias_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
-                      const float* __restrict__ bias, int m_bound, const int32_t* __restrict__ m_valid, int N, int K,
-                      int dbg, __half* __restrict__ c_out, int n_stages) {
+                      const __grid_constant__ CUtensorMap map_c, const float* __restrict__ bias, int m_bound,
+                      const int32_t* __restrict__ m_valid, int N, int K, int dbg, __half* __restrict__ c_out, int n_stages) {
   extern __shared__ unsigned char smem_raw[];
   constexpr int GKE = 2 * GK;                       // halves per 128-byte k-block
   constexpr int STAGE_B = WRES ? G_A_BYTES : G_STAGE_BYTES;
@@ -501,18 +544,20 @@ gemm_bias_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
       }
       ptx::mbar_wait(acc_full + buf, aph);
       ptx::tc_fence_after_sync();
-#pragma unroll 1
-      for (int ch = 0; ch < 2 * GN / GP_HALF; ++ch) {       // four 64-column pieces of the 256-column block
-        const int n0 = nt0 + ch * GP_HALF;
-        f16_half_to_stage(tmem_base + buf * GP_ACC_COLS + ch * GP_HALF, q, r_in_tile, my_stage, bias_sm + ch * GP_HALF,
-                          ch == 2 * GN / GP_HALF - 1, [&]() {
-          ptx::tc_fence_before_sync();                    // last read of this accumulator: hand it back
-          __syncwarp();
-          if (lane == 0) {
-            if (leader) ptx::mbar_arrive(acc_empty + buf);
-            else ptx::mbar_arrive_cluster(ptx::mapa(ptx::smem_u32(acc_empty + buf), 0u));
-          }
-        });
+      // Four 64-column pieces of the 256-column block, software-pipelined: the tcgen05.ld of piece c + 1 is in flight
+      // while piece c is converted, staged and stored (TMEM reads run at 64 B/clk per SM: 512 cycles per piece that
+      // used to sit in front of every conversion; r2 ncu of the K = 200 layer: epilogue groups, not MMAs or DRAM, set
+      // the tile rate).  Debug bit 18: the un-pipelined loop (A/B).
+      const uint32_t acc_col0 = tmem_base + buf * GP_ACC_COLS + ((uint32_t)(q * 32) << 16);
+      auto release = [&]() {
+        ptx::tc_fence_before_sync();                      // last read of this accumulator: hand it back
+        __syncwarp();
+        if (lane == 0) {
+          if (leader) ptx::mbar_arrive(acc_empty + buf);
+          else ptx::mbar_arrive_cluster(ptx::mapa(ptx::smem_u32(acc_empty + buf), 0u));
+        }
+      };
+      auto store_piece = [&](int n0) {
         ptx::named_bar_sync(1 + grp, 128);
         if (!(dbg & 2048)) {
           // 128-byte row segments: eight lanes per row, four rows per warp instruction
@@ -527,10 +572,42 @@ gemm_bias_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
           }
         }
         ptx::named_bar_sync(1 + grp, 128);                // staging is free again
+      };
+      uint32_t r0[2][32], r1[2][32];
+      ptx::tmem_ld_32x32(acc_col0, r0[0]);
+      ptx::tmem_ld_32x32(acc_col0 + 32, r1[0]);
+#pragma unroll
+      for (int ch = 0; ch < 2 * GN / GP_HALF; ++ch) {
+        ptx::tmem_ld_wait();
+        if (ch + 1 < 2 * GN / GP_HALF) {
+          ptx::tmem_ld_32x32(acc_col0 + (ch + 1) * GP_HALF, r0[(ch + 1) & 1]);
+          ptx::tmem_ld_32x32(acc_col0 + (ch + 1) * GP_HALF + 32, r1[(ch + 1) & 1]);
+        } else {
+          release();
+        }
+        if (dbg & (1 << 18)) {                              // debug bit 18 (A/B): row-major staging + coalesced stores
+          f16_regs_to_stage(r0[ch & 1], r1[ch & 1], r_in_tile, my_stage, bias_sm + ch * GP_HALF);
+          store_piece(nt0 + ch * GP_HALF);
+        } else {
+          // The piece leaves through ONE TMA store from a swizzled staging tile instead of 16 LDS + STG per thread;
+          // the copy engine writes while the next piece is converted (r2 probe, 505 k tokens: K = 200 0.449 -> 0.419 ms,
+          // K = 512 0.726 -> 0.671 ms).  Rows between the valid count and the end of the tile are written too
+          // (caller-owned, never read), like the tf32 kernel's stores.
+          if (q == 0 && lane == 0) ptx::bulk_wait_group_read<0>();      // the previous store has read the staging tile
+          ptx::named_bar_sync(1 + grp, 128);
+          f16_regs_to_swizzled(r0[ch & 1], r1[ch & 1], r_in_tile, my_stage, bias_sm + ch * GP_HALF);
+          ptx::fence_proxy_async_smem();
+          ptx::named_bar_sync(1 + grp, 128);
+          if (q == 0 && lane == 0 && !(dbg & 2048)) {
+            ptx::tma_store_2d(&map_c, my_stage, nt0 + ch * GP_HALF, m0);
+            ptx::bulk_commit_group();
+          }
+        }
       }
     }
   }
 
+  if (warp >= 4 && ((warp - 4) & 3) == 0 && lane == 0) ptx::bulk_wait_group<0>();    // (TMA-store variant) stores complete
   ptx::tc_fence_before_sync();
   ptx::cluster_sync();                    // the peer's MMAs / commits / remote arrives no longer target this CTA
   if (warp == 2) ptx::tmem_dealloc_2cta(tmem_base, GP_TMEM_COLS);
@@ -658,8 +735,8 @@ extern "C" int ttr_gemm_f16_bias(const void* A16, const void* W16, const float* 
     cfg.numAttrs = 1;
     int dbgv = g_debug_flags, stp = STP;
     __half* c16 = reinterpret_cast<__half*>(C16);
-    void* args[] = {(void*)&map_a, (void*)&map_w, (void*)&bias, (void*)&m_bound, (void*)&m_valid, (void*)&N, (void*)&K,
-                    (void*)&dbgv, (void*)&c16, (void*)&stp};
+    void* args[] = {(void*)&map_a, (void*)&map_w, (void*)&map_c, (void*)&bias, (void*)&m_bound, (void*)&m_valid, (void*)&N,
+                    (void*)&K, (void*)&dbgv, (void*)&c16, (void*)&stp};
     TTR_CHECK_CUDA(cudaLaunchKernelExC(&cfg, kern, args));
     return TTR_OK;
   }

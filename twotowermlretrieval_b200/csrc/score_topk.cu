@@ -324,14 +324,36 @@ __device__ __forceinline__ void merge_peers_body(const PeerLists& pl, int P, int
   int32_t tau_i = IDX_PAD;
   int cnt = 0;
   const int total = P * kin;
-  for (int t0 = warp * 32; t0 < total; t0 += SC_THREADS) {
+  // Every candidate of the query is fetched ONCE, all loads of a thread in flight together (ids and scores are
+  // independent loads, up to MG_U of each per thread), and the ids are kept in shared memory for the output phase.
+  // The first version read id -> (if valid) score per 256 candidates and the ids again at the end: five dependent
+  // round trips over NVLink (~2-3 us each) per query at 8 ranks; now it is one.
+  constexpr int MG_U = MAX_PEERS * TOPK_KMAX / SC_THREADS;
+  __shared__ int64_t cand_id[MAX_PEERS * TOPK_KMAX];
+  float pre_s[MG_U];
+  int64_t pre_i[MG_U];
+#pragma unroll
+  for (int u = 0; u < MG_U; ++u) {
+    const int t = warp * 32 + u * SC_THREADS + lane;
+    pre_s[u] = -INFINITY;
+    pre_i[u] = -1;
+    if (t < total) {
+      const int p = t / kin, j = t % kin;
+      pre_i[u] = __ldcg(pl.i[p] + (int64_t)q * kin + j);
+      pre_s[u] = __ldcg(pl.s[p] + (int64_t)q * kin + j);
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < MG_U; ++u) {
+    const int t0 = warp * 32 + u * SC_THREADS;
+    if (t0 >= total) break;                                   // warp-uniform
     const int t = t0 + lane;
     float s = -INFINITY;
     int32_t src = IDX_PAD;
     if (t < total) {
-      const int p = t / kin, j = t % kin;
-      if (__ldcg(pl.i[p] + (int64_t)q * kin + j) >= 0) {
-        s = __ldcg(pl.s[p] + (int64_t)q * kin + j);
+      cand_id[t] = pre_i[u];
+      if (pre_i[u] >= 0) {
+        s = pre_s[u];
         src = t;
       }
     }
@@ -367,7 +389,7 @@ __device__ __forceinline__ void merge_peers_body(const PeerLists& pl, int P, int
     const bool valid = src != IDX_PAD;
     const int p = valid ? src / kin : 0, e = valid ? src % kin : 0;
     out_s[(int64_t)q * k + j] = mrg_s[j];
-    out_i[(int64_t)q * k + j] = valid ? __ldcg(pl.i[p] + (int64_t)q * kin + e) : (int64_t)-1;
+    out_i[(int64_t)q * k + j] = valid ? cand_id[src] : (int64_t)-1;
     if (out_t) out_t[(int64_t)q * k + j] = (valid && pl.t[p]) ? __ldcg(pl.t[p] + (int64_t)q * kin + e) : 0.0;
   }
 }
@@ -493,7 +515,7 @@ extern "C" int ttr_topk_merge_peers(const uint64_t* peer_scores_h, const uint64_
                                     int64_t* out_idx, double* out_tfidf, void* stream) {
   using namespace ttr;
   TTR_REQUIRE(k >= 1 && k <= TOPK_KMAX, "ttr_topk_merge_peers: k=%d outside [1, %d]", k, TOPK_KMAX);
-  TTR_REQUIRE(P >= 1 && P <= MAX_PEERS && B >= 1 && kin >= 1, "ttr_topk_merge_peers: bad shape (P=%d)", P);
+  TTR_REQUIRE(P >= 1 && P <= MAX_PEERS && B >= 1 && kin >= 1 && kin <= TOPK_KMAX, "ttr_topk_merge_peers: bad shape (P=%d, kin=%d)", P, kin);
   PeerLists pl;
   for (int p = 0; p < MAX_PEERS; ++p) {
     pl.s[p] = p < P ? reinterpret_cast<const float*>(peer_scores_h[p]) : nullptr;
@@ -511,7 +533,7 @@ extern "C" int ttr_topk_exchange_merge(const uint64_t* peer_scores_h, const uint
                                        double* out_tfidf, void* stream) {
   using namespace ttr;
   TTR_REQUIRE(k >= 1 && k <= TOPK_KMAX, "ttr_topk_exchange_merge: k=%d outside [1, %d]", k, TOPK_KMAX);
-  TTR_REQUIRE(P >= 1 && P <= MAX_PEERS && B >= 1 && kin >= 1, "ttr_topk_exchange_merge: bad shape (P=%d)", P);
+  TTR_REQUIRE(P >= 1 && P <= MAX_PEERS && B >= 1 && kin >= 1 && kin <= TOPK_KMAX, "ttr_topk_exchange_merge: bad shape (P=%d, kin=%d)", P, kin);
   TTR_REQUIRE(my_rank >= 0 && my_rank < P, "ttr_topk_exchange_merge: rank %d outside [0, %d)", my_rank, P);
   PeerLists pl;
   PeerFlags pf;
