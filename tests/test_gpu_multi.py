@@ -59,6 +59,24 @@ def _worker(rank, world, port, q):
             s, i = idx.search(Q, 50)
             ok &= bool(torch.equal(i, i1))
         out["search_skewed"] = ok
+        # deferred merges (side stream, three rotating buffers): a stream of 12 different batches enqueued without
+        # waiting for any result, one rank delayed every few steps, interleaved with synchronous calls and a hybrid
+        # call on the same exchange -> every result equals the single-device one
+        Qs = [torch.tensor(synth.make_unit_rows(33, 256, seed=300 + j), device=dev) for j in range(12)]
+        want = [search_topk(q_, D, 50) for q_ in Qs]
+        for rnd in range(2):
+            pend = []
+            for j, q_ in enumerate(Qs):
+                if rank == j % world and j % 3 == 0:
+                    torch.cuda._sleep(int(5e7))
+                if j == 7 and rnd == 1:
+                    s_sync, i_sync = idx.search(Qs[0], 50)              # a synchronous call in the middle of the stream
+                    ok &= bool(torch.equal(i_sync, want[0][1]))
+                pend.append(idx.search_deferred(q_, 50))
+            for (ws_, wi_), p_ in zip(want, pend):
+                s_, i_ = p_.result()
+                ok &= bool(torch.equal(i_, wi_) and torch.allclose(s_, ws_, atol=1e-6))
+        out["search_deferred"] = ok
         Q = torch.tensor(synth.make_unit_rows(5, 256, seed=9), device=dev)
         h = idx.search_hybrid(Q, qcsr, alpha=0.4, k=50, top_n=10)
         s1, i1 = search_topk(Q, D, 50)
@@ -153,6 +171,7 @@ def test_sharded_search_hybrid_keyword_and_dp_training(world):
     for rank in range(world):
         r = res[rank]
         assert r["search3"] and r["search40"] and r["search200"] and r["search_skewed"] and r["hybrid"] and r["keyword"], r
+        assert r["search_deferred"], r
         assert r["peer_memory"], "symmetric-memory exchange was not active"
         # all-reduce(SUM) / world of the per-rank mean-loss gradients == gradient of the global-batch mean loss, up to
         # the fp32/tf32 summation order of the kernels (different row tilings): 2e-3 of each tensor's largest entry.

@@ -171,6 +171,13 @@ def test_sharded_equals_unsharded(cuda_device):
         parts.append(search_topk(Qd, Dd[lo:hi].contiguous(), 50, row_offset=lo))
     ms, mi = topk_merge(torch.stack([p[0] for p in parts]), torch.stack([p[1] for p in parts]), 50)
     assert torch.equal(mi, i_full) and torch.equal(ms, s_full)
+    # one process: the deferred entry point is the plain search behind the same handle type
+    from twotowermlretrieval_b200.index import PendingSearch, ShardedIndex
+    pend = ShardedIndex(Dd).search_deferred(Qd, 50)
+    assert isinstance(pend, PendingSearch)
+    s_d, i_d = pend.result()
+    assert torch.equal(i_d, i_full) and torch.equal(s_d, s_full)
+    assert pend.result()[0] is s_d                                 # idempotent
 
 
 def test_million_docs_properties(cuda_device):

@@ -207,15 +207,40 @@ def shard_bounds(n_rows: int, world: int, rank: int) -> Tuple[int, int]:
     return lo, min(n_rows, lo + per)
 
 
+class PendingSearch:
+    """Result of a search whose cross-rank merge runs on the exchange's side stream.  `result()` makes the caller's
+    current stream wait for it and returns the tensors; until then the caller's stream is free to start the next
+    scan (`ShardedIndex.search_deferred`)."""
+
+    def __init__(self, tensors, event=None):
+        self._tensors, self._event = tensors, event
+
+    def result(self):
+        if self._event is not None:
+            cur = torch.cuda.current_stream(self._tensors[0].device)
+            cur.wait_event(self._event)
+            for t in self._tensors:
+                if t is not None:
+                    t.record_stream(cur)
+            self._event = None
+        return self._tensors
+
+
 class _PeerExchange:
     """Symmetric-memory candidate buffers: every rank writes its local [B, k] top-k (scores, global
     ids, optional TF-IDF payload) into its own buffer; ONE kernel per step then signals the peers,
     waits for their signals (release/acquire flags in the same symmetric allocation) and merges all
     R lists in place over NVLink (ttr_topk_exchange_merge) — no all-gather, no separate barrier launch.
-    Two list buffers alternate by step parity so a fast rank never overwrites what a slow peer is
-    still reading (a rank can be at most one step ahead: it waits for every peer's flag of its step)."""
+
+    The merge kernel runs on a SIDE STREAM behind the scan of its step, and THREE list buffers rotate: the scan
+    of step s writes buffer s mod 3, last read by the peers' merges of step s - 3.  Those are finished once this
+    rank's merge of step s - 2 has completed (it waited for every peer's flag of step s - 2, which a peer raises in
+    its merge kernel of that step, i.e. after its merge of step s - 3 on the same stream) — so the scan of step s
+    only waits for that event, and a rank whose peers are late runs one scan ahead instead of spinning in the merge
+    (`search_deferred`; at 8 GPUs the synchronous step spent 41 us behind a 231 us scan in exchange + rank skew)."""
 
     FLAG_BYTES = 256
+    NBUF = 3
 
     def __init__(self, group, device, max_b: int, k: int):
         import ctypes
@@ -228,8 +253,8 @@ class _PeerExchange:
         n = max_b * k
         self.off_s, self.off_i, self.off_t = 0, n * 4, n * 12
         self.stride = (n * 20 + 255) // 256 * 256
-        self.off_flags = 2 * self.stride
-        self.buf = symm.empty(2 * self.stride + self.FLAG_BYTES, dtype=torch.uint8, device=device)
+        self.off_flags = self.NBUF * self.stride
+        self.buf = symm.empty(self.NBUF * self.stride + self.FLAG_BYTES, dtype=torch.uint8, device=device)
         grp = group if group is not None else dist.group.WORLD
         self.hdl = symm.rendezvous(self.buf, grp)
         self.ptrs = [int(p) for p in self.hdl.buffer_ptrs]
@@ -240,31 +265,61 @@ class _PeerExchange:
         arr = ctypes.c_uint64 * self.world
         self._arr = arr
         self._flags = arr(*[a + self.off_flags for a in self.ptrs])
+        self.merge_stream = torch.cuda.Stream(device=device)
+        self._merged = {}                      # step -> event recorded behind that step's merge kernel
 
     def views(self, B: int):
-        p = (self.step + 1) & 1                # the buffer of the step that `merge` is about to run
-        base = p * self.stride
+        """Views of the buffer the NEXT step's scan writes; the caller's stream first waits until the peers can no
+        longer be reading it (this rank's merge of two steps ago has completed)."""
+        s = self.step + 1
+        ev = self._merged.get(s - 2)
+        if ev is not None:
+            torch.cuda.current_stream(self.buf.device).wait_event(ev)
+        base = (s % self.NBUF) * self.stride
         n = B * self.k
         s = self.buf[base + self.off_s: base + self.off_s + n * 4].view(torch.float32).view(B, self.k)
         i = self.buf[base + self.off_i: base + self.off_i + n * 8].view(torch.int64).view(B, self.k)
         t = self.buf[base + self.off_t: base + self.off_t + n * 8].view(torch.float64).view(B, self.k)
         return s, i, t
 
-    def merge(self, B: int, with_tfidf: bool):
-        """One kernel: signal, wait for the peers, read every rank's lists over peer memory, merge."""
+    def merge(self, B: int, with_tfidf: bool, deferred: bool = False):
+        """One kernel on the side stream, behind everything the caller's stream has enqueued so far (the scan that
+        filled this step's buffer): signal, wait for the peers, read every rank's lists over peer memory, merge.
+        Returns (scores, ids, tfidf) — or, with `deferred`, a PendingSearch of them."""
         ct = self.ctypes
         self.step += 1
-        base = (self.step & 1) * self.stride
+        s = self.step
+        base = (s % self.NBUF) * self.stride
         ps = self._arr(*[a + base + self.off_s for a in self.ptrs])
         pi = self._arr(*[a + base + self.off_i for a in self.ptrs])
         pt = self._arr(*[a + base + self.off_t for a in self.ptrs]) if with_tfidf else None
         dev = self.buf.device
-        out_s = torch.empty(B, self.k, dtype=torch.float32, device=dev)
-        out_i = torch.empty(B, self.k, dtype=torch.int64, device=dev)
-        out_t = torch.empty(B, self.k, dtype=torch.float64, device=dev) if with_tfidf else None
-        _lib.call("ttr_topk_exchange_merge", ct.addressof(ps), ct.addressof(pi), ct.addressof(pt) if pt else None,
-                  ct.addressof(self._flags), self.world, self.rank, self.step & 0xFFFFFFFF, B, self.k, self.k,
-                  out_s, out_i, out_t)
+        cur = torch.cuda.current_stream(dev)
+        # synchronous calls stay on the caller's stream (no cross-stream hop on the latency path); merges must run in
+        # step order on every rank, so such a call first waits for a still pending deferred merge
+        run_on = self.merge_stream if deferred else cur
+        if deferred:
+            scanned = torch.cuda.Event()
+            scanned.record(cur)
+        else:
+            prev = self._merged.get(s - 1)
+            if prev is not None:
+                cur.wait_event(prev)
+        with torch.cuda.stream(run_on):
+            if deferred:
+                self.merge_stream.wait_event(scanned)
+            out_s = torch.empty(B, self.k, dtype=torch.float32, device=dev)
+            out_i = torch.empty(B, self.k, dtype=torch.int64, device=dev)
+            out_t = torch.empty(B, self.k, dtype=torch.float64, device=dev) if with_tfidf else None
+            _lib.call("ttr_topk_exchange_merge", ct.addressof(ps), ct.addressof(pi), ct.addressof(pt) if pt else None,
+                      ct.addressof(self._flags), self.world, self.rank, s & 0xFFFFFFFF, B, self.k, self.k,
+                      out_s, out_i, out_t)
+            done = torch.cuda.Event()
+            done.record(run_on)
+        self._merged[s] = done
+        self._merged.pop(s - 3, None)
+        if deferred:
+            return PendingSearch((out_s, out_i, out_t), done)
         return out_s, out_i, out_t
 
 
@@ -300,6 +355,9 @@ class ShardedIndex:
         if self._px is None or self._px.k != k or self._px.max_b < B:
             dist = self._dist
             dev = self.docs.device
+            if self._px is not None:               # growth: nothing of the old exchange may still be in flight here
+                self._px.merge_stream.synchronize()
+                torch.cuda.current_stream(dev).synchronize()
             ok, err = 1, None
             try:
                 px = _PeerExchange(self.group, dev, max(B, 128), k)
@@ -332,6 +390,22 @@ class ShardedIndex:
                 return out
             return s, i
         return search_topk(Q, self.docs, k, self.row_offset, out=out)
+
+    def search_deferred(self, Q: torch.Tensor, k: int = 50) -> PendingSearch:
+        """`search` for a stream of independent query batches: the local scan is enqueued on the caller's stream,
+        the cross-rank exchange + merge on a side stream, and the call returns a PendingSearch whose `result()`
+        gives (scores, ids).  The caller may enqueue the next batch right away; a rank whose peers are still
+        scanning runs one scan ahead instead of waiting in the merge.  Same results as `search`."""
+        if Q.dim() == 1:
+            Q = Q.unsqueeze(0)
+        B = Q.shape[0]
+        px = self._exchange(B, k) if self.world > 1 else None
+        if px is None:
+            return PendingSearch(self.search(Q, k))
+        vs, vi, _ = px.views(B)
+        self._local(Q, k, out=(vs, vi))
+        pend = px.merge(B, with_tfidf=False, deferred=True)
+        return PendingSearch(pend._tensors[:2], pend._event)
 
     def search(self, Q: torch.Tensor, k: int = 50):
         if self.world == 1:
