@@ -18,7 +18,7 @@ flat, lens = synth.make_ragged_tokens(n, "passage", cfg["VOCAB_SIZE"], seed=2)
 out = torch.empty(n, 256, device=dev)
 encode_rows(enc, (flat[: int(lens[:4096].sum())], lens[:4096]), dev, out=out)
 torch.cuda.synchronize()
-for lanes, max_tokens, max_rows in ((1, 524288, 15360), (1, 1048576, 15360), (1, 1048576, 30720), (1, 262144, 7680), (1, 524288, 15360)):
+for lanes, max_tokens, max_rows in ((1, 1048576, 30720), (1, 2097152, 61440), (1, 4194304, 122880), (1, 1048576, 30720)):
     smp = bench.ClockSampler(0); smp.start()
     t0 = time.perf_counter()
     encode_rows(enc, (flat, lens), dev, out=out, streams=lanes, max_tokens=max_tokens, max_rows=max_rows)
