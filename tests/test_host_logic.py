@@ -296,3 +296,25 @@ def test_plan_batches_rounds_rows_to_whole_recurrence_waves():
     assert bounds[0][0] == 0 and bounds[-1][1] == 60000
     for lo, hi in bounds[:-1]:
         assert (hi - lo) % ROW_QUANTUM == 0 or hi - lo < ROW_QUANTUM
+
+
+def test_plan_batches_radix_order_equals_the_stable_descending_sort():
+    """`plan_batches` sorts 16-bit keys (numpy's radix path) when every length fits; the order must be the stable
+    descending-length order of the general path, and lengths >= 65536 must fall back to it."""
+    rng = np.random.default_rng(5)
+    for hi in (40, 300, 70000):
+        lengths = rng.integers(1, hi, size=5000).astype(np.int64)
+        order, bounds = plan_batches(lengths, max_tokens=1 << 20, max_rows=30720)
+        np.testing.assert_array_equal(order, np.argsort(-lengths, kind="stable"))
+        assert bounds[0][0] == 0 and bounds[-1][1] == 5000 and all(a[1] == b[0] for a, b in zip(bounds, bounds[1:]))
+        for lo, hi_ in bounds:                       # a batch never exceeds the padded-token budget (one row always fits)
+            assert (hi_ - lo) * int(lengths[order[lo]]) <= (1 << 20) or hi_ - lo == 1
+
+
+def test_bench_reads_roofline_traffic_from_the_committed_capture_and_says_so():
+    import bench
+    t = bench.committed_traffic(8841823, 128, 1)
+    assert t["traffic"] is not None and 0.99 < t["traffic"] / (8841823 * 1024) < 1.02      # DRAM bytes == algorithmic bytes
+    assert "COMMITTED CAPTURE" in t["traffic_note"] and "not measured in this run" in t["traffic_note"]
+    assert bench.committed_traffic(8841823, 128, 8)["traffic"] is None                     # another shape: null, not a guess
+    assert bench.committed_traffic(12345, 7, 1)["traffic"] is None

@@ -242,11 +242,25 @@ __device__ __forceinline__ float kth_largest_128(float* smem_f, uint32_t* scratc
   uint32_t* keys = reinterpret_cast<uint32_t*>(smem_f);
   int finite = 0;
   uint32_t kmax = 0u;
-  for (int i = tid; i < n; i += SM_MQ) {
-    const float v = __ldcg(src + i);
-    keys[i] = f2key(v);
-    kmax = max(kmax, keys[i]);
-    finite += v > -INFINITY ? 1 : 0;
+  // eight independent loads per thread in flight (148 slices x 4 values = 592 = 4.6 per thread: as a plain loop these
+  // were five dependent L2 round trips in the middle of the grid-barrier phase, during which no CTA streams documents)
+  for (int i0 = 0; i0 < n; i0 += 8 * SM_MQ) {
+    float v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int i = i0 + u * SM_MQ + tid;
+      v[u] = i < n ? __ldcg(src + i) : -INFINITY;
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int i = i0 + u * SM_MQ + tid;
+      if (i < n) {
+        const uint32_t key = f2key(v[u]);
+        keys[i] = key;
+        kmax = max(kmax, key);
+        finite += v[u] > -INFINITY ? 1 : 0;
+      }
+    }
   }
   if (tid == 0) { s_prefix = 0u; s_rem = (uint32_t)k; }
   // count finite values across the 128 threads through the histogram array (hist[1]: the largest key)
@@ -437,21 +451,34 @@ scorer_body(const float* __restrict__ Q, const CUtensorMap& map_d, int B, int64_
   const uint32_t tmem_acc = tmem_base + SM_Q_COLS;
 
   // ---- stage the query tile into tensor memory: thread (warp 4+w, lane) owns TMEM lane 32w+lane
+  // (r2: splitting the columns over the keeper and the screener warp of a quarter and letting the TMA producer start
+  // before this barrier did not help — 18.1 k instead of 13.8 k cycles until "queries staged", kernel 322.9 k vs 320.0 k)
   if (warp >= 4 && warp < 8) {
     const int qw = warp - 4;
     const int q = q0 + qw * 32 + lane;
     // initial screening threshold: the seeded global bound (main pass), "anything" while a sample top-4 is empty,
     // +inf for the padding queries of the last tile
     thr_sh[qw * 32 + lane] = q >= B ? INFINITY : (MODE == 0 ? __ldcg(tau_g + q) : -3.402823466e38f);
-    const float4* src = reinterpret_cast<const float4*>(Q + (int64_t)(q < B ? q : 0) * SM_DIM);
-    // two round trips of 32 independent 16-byte loads each (the row is 1 KB; eight dependent
-    // round trips of 8 loads cost ~8 us of the ~30 us fixed cost of a launch)
+    // Two rounds of 128 columns.  Loads are COALESCED — instruction i of a warp reads the 512-byte segment of row i of
+    // its quarter, lane = 16-byte chunk — and transposed through a warp-private scratch in the (still idle) ring so that
+    // lane r ends up with row r: a thread reading its own 1 KB row issued 32-line requests per instruction, 8,192 line
+    // requests per CTA, and the prologue was bound by their throughput (13.8 k cycles to "queries staged").
+    unsigned char* scratch = ring + qw * (32 * 528);                 // 32 rows x (512 B + 16 B pad): conflict-free both ways
 #pragma unroll 1
     for (int c0 = 0; c0 < SM_DIM; c0 += 128) {
       float4 x[32];
 #pragma unroll
-      for (int v = 0; v < 32; ++v)
-        x[v] = (q < B) ? __ldg(src + (c0 >> 2) + v) : make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int i = 0; i < 32; ++i) {
+        const int qrow = q0 + qw * 32 + i;
+        x[i] = (qrow < B) ? __ldg(reinterpret_cast<const float4*>(Q + (int64_t)qrow * SM_DIM + c0) + lane)
+                          : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int i = 0; i < 32; ++i) *reinterpret_cast<float4*>(scratch + i * 528 + lane * 16) = x[i];
+      __syncwarp();
+#pragma unroll
+      for (int v = 0; v < 32; ++v) x[v] = *reinterpret_cast<const float4*>(scratch + lane * 528 + v * 16);
+      __syncwarp();
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
         uint32_t r[32];
@@ -466,6 +493,7 @@ scorer_body(const float* __restrict__ Q, const CUtensorMap& map_d, int B, int64_
       }
     }
     ptx::tmem_st_wait();
+    ptx::fence_proxy_async_smem();           // the scratch is ring space: generic writes before the TMA (async proxy) fills it
   }
   ptx::tc_fence_before_sync();
   // pair: the leader's MMAs read the PEER's staged queries and signal its barriers too -> cluster-wide barrier
