@@ -203,3 +203,13 @@ def test_bulk_encode_matches_per_batch_encode(cuda_device):
             assert torch.equal(e, m.encode_document(b))
     with pytest.raises(RuntimeError):
         encode_rows(m.doc_encoder, rows[:3] + [[]], cuda_device)
+    with pytest.raises(RuntimeError):                      # ids that are all 0 ("the"): zero effective length (quirk #2),
+        encode_rows(m.doc_encoder, rows[:40] + [[0, 0, 0]] + rows[40:80], cuda_device)   # found by the packer's count
+    # a zero in the middle of a row only shortens it (quirk #1); the packed token bound comes from the packer's count
+    odd = [list(r) for r in rows[:64]]
+    odd[5][1] = 0
+    got = encode_rows(m.doc_encoder, odd, cuda_device, max_tokens=2048, max_rows=32)
+    with torch.no_grad():
+        T = max(len(r) for r in odd)
+        pad = torch.tensor([r + [0] * (T - len(r)) for r in odd], device=cuda_device)
+        assert torch.allclose(got, m.encode_document(pad), atol=2e-6)
