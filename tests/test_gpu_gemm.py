@@ -130,7 +130,8 @@ def test_f16_pair_gemm_matches_fp64_and_the_single_cta_kernel(cuda_device, M, N,
     b = torch.randn(N, device=cuda_device, generator=g) * 0.05
     mvt = None if mv is None else torch.tensor([mv], dtype=torch.int32, device=cuda_device)
     out = {}
-    for name, flags in (("pair", 0), ("single", 1 << 30), ("pair_streamed_w", 1 << 19), ("pair_coalesced_store", 1 << 18)):
+    for name, flags in (("pair", 0), ("single", 1 << 30), ("pair_streamed_w", 1 << 19), ("pair_coalesced_store", 1 << 18),
+                        ("pair_a_multicast", 1 << 16)):
         C = torch.full((M, N), 7.0, dtype=torch.float16, device=cuda_device)
         _lib.call_nostream("ttr_debug_set_flags", flags)
         try:
@@ -146,6 +147,7 @@ def test_f16_pair_gemm_matches_fp64_and_the_single_cta_kernel(cuda_device, M, N,
     assert float((err - ref.abs() * 2.0 ** -11).max()) <= 2e-6 * max(scale, 1.0), float(err.max())
     assert torch.equal(out["pair"][:rows], out["single"][:rows])
     assert torch.equal(out["pair"][:rows], out["pair_streamed_w"][:rows])
+    assert torch.equal(out["pair"][:rows], out["pair_a_multicast"][:rows])      # debug bit 16: clusters of four, A multicast to two pairs
     assert torch.equal(out["pair"][:rows], out["pair_coalesced_store"][:rows])  # debug bit 18: staged coalesced stores instead of TMA stores
     tail_lo = (rows + 255) // 256 * 256                    # rows of partially valid tiles may be written (caller-owned, never read)
     if tail_lo < M:

@@ -28,7 +28,7 @@ for K in (200, 512):
     C = torch.empty(M, 1536, dtype=torch.float16, device=dev)
     mv = torch.tensor([M], dtype=torch.int32, device=dev)
     for name, flags in (("default", 0), ("no stores (bit 11)", 2048), ("pair, W streamed (bit 19)", 1 << 19), ("single CTA (bit 30)", 1 << 30),
-                        ("single CTA, no stores", (1 << 30) | 2048), ("coalesced-store epilogue (bit 18)", 1 << 18)):
+                        ("single CTA, no stores", (1 << 30) | 2048), ("coalesced-store epilogue (bit 18)", 1 << 18), ("clusters of 4, A multicast (bit 16)", 1 << 16)):
         _lib.call_nostream("ttr_debug_set_flags", flags)
         ms = timed(lambda: _lib.call("ttr_gemm_f16_bias", X, W, b, C, M, mv, 1536, K))
         _lib.call_nostream("ttr_debug_set_flags", 0)

@@ -401,7 +401,14 @@ __device__ __forceinline__ void f16_regs_to_swizzled(const uint32_t (&ra)[32], c
   }
 }
 
-template <bool WRES>
+// CL4 = true (with WRES; debug bit 16, NOT the default — measured slower, see the host code): clusters of FOUR CTAs =
+// two pairs that share a 256-row block of A and own two adjacent
+// 256-column tiles.  Each k-block of A is loaded ONCE per cluster row half — pair 0's CTA r issues the even k-blocks,
+// pair 1's CTA r the odd ones — and multicast into both pairs' rings (`cp.async.bulk.tensor ... multicast::cluster`), so
+// an SM requests half the A bytes per MMA: at K = 200 the A tile is re-read by six pairs and, together with the gi
+// stores, the L2 <-> SM fabric was the limit (r2 probe: 0.42 ms with stores, 0.29 without, MMA floor 0.14 per 505 k tokens).
+// A stage is refilled when BOTH pairs' MMAs have retired (`empty` counts two commits, each multicast to all four CTAs).
+template <bool WRES, bool CL4>
 __global__ void __launch_bounds__(G_THREADS, 1)
 gemm_bias_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
                       const __grid_constant__ CUtensorMap map_c, const float* __restrict__ bias, int m_bound,
@@ -421,17 +428,26 @@ gemm_bias_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
   uint64_t* w_full = acc_empty + 2;                 // WRES: this CTA's resident W rows have landed
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_full + 1);
 
+  static_assert(!CL4 || WRES, "the A-multicast variant keeps W resident");
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t rank = ptx::cluster_ctarank();
+  const uint32_t crank = ptx::cluster_ctarank();        // 0..1 (one pair) or 0..3 (two pairs)
+  const uint32_t rank = crank & 1u;                     // rank inside the pair
+  const uint32_t pr = CL4 ? (crank >> 1) : 0u;          // which pair of the cluster
+  const uint32_t lead = crank & ~1u;                    // cluster rank of this pair's leader
   const bool leader = rank == 0u;
   const int M = m_valid ? min(m_bound, *m_valid) : m_bound;
   const int m_tiles = ceil_div(M, 2 * GM), n_tiles = ceil_div(N, 2 * GN);
-  const int total_tiles = m_tiles * n_tiles;
-  const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+  // work units: (256-row block, column tile) per pair, or (256-row block, two adjacent column tiles) per cluster of four
+  const int n_units = CL4 ? n_tiles / 2 : n_tiles;
+  const int total_tiles = m_tiles * n_units;
+  const int pair = CL4 ? blockIdx.x >> 2 : blockIdx.x >> 1;
+  const int n_pairs = CL4 ? gridDim.x >> 2 : gridDim.x >> 1;
+  auto col_tile = [&](int tile) { return CL4 ? (tile % n_units) * 2 + (int)pr : tile % n_units; };
+  auto row_tile = [&](int tile) { return tile / n_units; };
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < n_stages; ++s) {
-      ptx::mbar_init(full_bar + s, 1); ptx::mbar_init(empty_bar + s, 1); ptx::mbar_init(peer_full + s, 1);
+      ptx::mbar_init(full_bar + s, 1); ptx::mbar_init(empty_bar + s, CL4 ? 2 : 1); ptx::mbar_init(peer_full + s, 1);
     }
     for (int b = 0; b < 2; ++b) { ptx::mbar_init(acc_full + b, 1); ptx::mbar_init(acc_empty + b, 8); }
     ptx::mbar_init(w_full, 1);
@@ -453,14 +469,14 @@ gemm_bias_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
       ptx::prefetch_tensormap(&map_w);
     }
     if (WRES && pair < total_tiles && ptx::elect_one()) {
-      const int n0 = (pair % n_tiles) * 2 * GN + (int)rank * GN;      // constant for this pair: n_pairs % n_tiles == 0
+      const int n0 = col_tile(pair) * 2 * GN + (int)rank * GN;        // constant for this pair: n_pairs % n_units == 0
       ptx::mbar_arrive_expect_tx(w_full, (uint32_t)(k_blocks * G_B_BYTES));
       for (int kb = 0; kb < k_blocks; ++kb) ptx::tma_load_2d(w_res + kb * G_B_BYTES, &map_w, kb * GKE, n0, w_full);
     }
     __syncwarp();
     int it = 0;
     for (int tile = pair; tile < total_tiles; tile += n_pairs) {
-      const int m0 = (tile / n_tiles) * 2 * GM + (int)rank * GM, n0 = (tile % n_tiles) * 2 * GN + (int)rank * GN;
+      const int m0 = row_tile(tile) * 2 * GM + (int)rank * GM, n0 = col_tile(tile) * 2 * GN + (int)rank * GN;
       for (int kb = 0; kb < k_blocks; ++kb, ++it) {
         const int s = it % n_stages;
         const uint32_t ph = (uint32_t)(it / n_stages) & 1u;
@@ -468,8 +484,15 @@ gemm_bias_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
         unsigned char* a_dst = tiles + s * STAGE_B;
         if (ptx::elect_one()) {
           ptx::mbar_arrive_expect_tx(full_bar + s, STAGE_B);
-          ptx::tma_load_2d(a_dst, &map_a, kb * GKE, m0, full_bar + s);
-          if (!WRES) ptx::tma_load_2d(a_dst + G_A_BYTES, &map_w, kb * GKE, n0, full_bar + s);
+          if (CL4) {
+            // the two CTAs with the same rank-in-pair read the same A rows: they take turns loading a k-block for both
+            // (data that lands in the other CTA before it has armed its barrier only drives its count negative)
+            if ((uint32_t)(it & 1) == pr)
+              ptx::tma_load_2d_multicast(a_dst, &map_a, kb * GKE, m0, full_bar + s, (uint16_t)((1u << rank) | (4u << rank)));
+          } else {
+            ptx::tma_load_2d(a_dst, &map_a, kb * GKE, m0, full_bar + s);
+            if (!WRES) ptx::tma_load_2d(a_dst + G_A_BYTES, &map_w, kb * GKE, n0, full_bar + s);
+          }
         }
         __syncwarp();
       }
@@ -500,8 +523,9 @@ gemm_bias_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
           for (int k = 0; k < GK / 8; ++k)
             if ((kb * (GK / 8) + k) * 16 < K)          // k-steps beyond K hold only zero fill (K = 200: 13 of 16)
               ptx::mma_f16_ss_2cta(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
-          ptx::mma_commit_2cta(empty_bar + s, 3);                      // both CTAs' stage s is free
-          if (kb == k_blocks - 1) ptx::mma_commit_2cta(acc_full + buf, 3);
+          // stage s is free in both CTAs of the pair (CL4: one of the two commits all four CTAs wait for)
+          ptx::mma_commit_2cta(empty_bar + s, CL4 ? (uint16_t)0xF : (uint16_t)3);
+          if (kb == k_blocks - 1) ptx::mma_commit_2cta(acc_full + buf, (uint16_t)(3u << lead));
         }
         __syncwarp();
       }
@@ -514,11 +538,11 @@ gemm_bias_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
       for (int kb = 0; kb < k_blocks; ++kb, ++it) {
         const int s = it % n_stages;
         ptx::mbar_wait(full_bar + s, (uint32_t)(it / n_stages) & 1u);
-        if (ptx::elect_one()) ptx::mbar_arrive_cluster(ptx::mapa(ptx::smem_u32(peer_full + s), 0u));
+        if (ptx::elect_one()) ptx::mbar_arrive_cluster(ptx::mapa(ptx::smem_u32(peer_full + s), lead));
         __syncwarp();
       }
   } else if (warp >= 4) {
-    // ===== epilogue: this CTA's 128 x 256 block, 128 columns at a time through the row-major fp16 staging =====
+    // ===== epilogue: this CTA's 128 x 256 block, four 64-column pieces through a staging tile =====
     const int grp = (warp - 4) >> 2;
     const int q = (warp - 4) & 3;                         // TMEM lane quadrant of this warp
     const int r_in_tile = q * 32 + lane;
@@ -531,7 +555,7 @@ gemm_bias_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
       const int buf = local & 1;
       if (buf != grp) continue;
       const uint32_t aph = (uint32_t)(local >> 1) & 1u;
-      const int m0 = (tile / n_tiles) * 2 * GM + (int)rank * GM, nt0 = (tile % n_tiles) * 2 * GN;
+      const int m0 = row_tile(tile) * 2 * GM + (int)rank * GM, nt0 = col_tile(tile) * 2 * GN;
       if (nt0 != bias_n0) {
         ptx::named_bar_sync(1 + grp, 128);                // nobody still reads the previous slice
 #pragma unroll
@@ -554,7 +578,7 @@ gemm_bias_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
         __syncwarp();
         if (lane == 0) {
           if (leader) ptx::mbar_arrive(acc_empty + buf);
-          else ptx::mbar_arrive_cluster(ptx::mapa(ptx::smem_u32(acc_empty + buf), 0u));
+          else ptx::mbar_arrive_cluster(ptx::mapa(ptx::smem_u32(acc_empty + buf), lead));
         }
       };
       auto store_piece = [&](int n0) {
@@ -712,17 +736,29 @@ extern "C" int ttr_gemm_f16_bias(const void* A16, const void* W16, const float* 
     const int STP = wres ? res_stages : GP_STAGES;
     const size_t smem_p = wres ? (size_t)k_blocks * G_B_BYTES + (size_t)STP * G_A_BYTES + 2 * (size_t)GP_STAGE + misc_p
                                : (size_t)STP * G_STAGE_BYTES + 2 * (size_t)GP_STAGE + misc_p;
-    const void* kern = wres ? (const void*)gemm_bias_pair_kernel<true> : (const void*)gemm_bias_pair_kernel<false>;
+    // debug bit 16 (A/B, weight-stationary shapes with an even number of column tiles): two pairs per cluster sharing
+    // (multicasting) the A block.  Measured SLOWER — 0.707 vs 0.421 ms per 505 k tokens at K = 200 (0.577 vs 0.286
+    // without the stores): halving the A requests does not pay for refilling a stage only after BOTH pairs have retired
+    // it and for the multicast's latency — so independent pairs stay the default.
+    const bool cl4 = wres && pn_tiles % 2 == 0 && pn_tiles / 2 <= sm_count() / 4 && (g_debug_flags & (1 << 16));
+    const void* kern = cl4 ? (const void*)gemm_bias_pair_kernel<true, true>
+                           : wres ? (const void*)gemm_bias_pair_kernel<true, false> : (const void*)gemm_bias_pair_kernel<false, false>;
     static thread_local int attr_dev = -1;
     int cur_dev = 0;
     TTR_CHECK_CUDA(cudaGetDevice(&cur_dev));
     if (attr_dev != cur_dev) {
-      TTR_CHECK_CUDA(cudaFuncSetAttribute(gemm_bias_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
-      TTR_CHECK_CUDA(cudaFuncSetAttribute(gemm_bias_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
+      TTR_CHECK_CUDA(cudaFuncSetAttribute(gemm_bias_pair_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
+      TTR_CHECK_CUDA(cudaFuncSetAttribute(gemm_bias_pair_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
+      TTR_CHECK_CUDA(cudaFuncSetAttribute(gemm_bias_pair_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
       attr_dev = cur_dev;
     }
     int pairs = std::max(1, std::min(pair_tiles, sm_count() / 2));
     if (wres) pairs = pn_tiles * std::max(1, std::min(sm_count() / 2 / pn_tiles, pm_tiles));   // multiple of the column tiles
+    const int cl_size = cl4 ? 4 : 2;
+    if (cl4) {                                            // clusters of four: a multiple of the column-tile PAIRS
+      const int groups = pn_tiles / 2;
+      pairs = 2 * groups * std::max(1, std::min(sm_count() / 4 / groups, pm_tiles));
+    }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(2 * pairs);
     cfg.blockDim = dim3(G_THREADS);
@@ -730,7 +766,7 @@ extern "C" int ttr_gemm_f16_bias(const void* A16, const void* W16, const float* 
     cfg.stream = (cudaStream_t)stream;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    at[0].val.clusterDim.x = cl_size; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at;
     cfg.numAttrs = 1;
     int dbgv = g_debug_flags, stp = STP;
