@@ -323,41 +323,6 @@ constexpr int GP_PITCH = GP_HALF * 2 + 16;                // staging row: 128 B 
 constexpr int GP_STAGE = GM * GP_PITCH;                   // 18 KB per epilogue group
 constexpr int GP_STAGES = 5;
 
-// fp16 epilogue of 128 rows x 64 columns: two double-buffered tcgen05.ld of 32 columns, bias from shared memory,
-// row-major fp16 staging (GP_PITCH).  `release` runs after the last tcgen05.ld when `last` is set.
-template <typename Release>
-__device__ __forceinline__ void f16_half_to_stage(uint32_t tmem_col0, int q, int r_in_tile, unsigned char* my_stage,
-                                                  const float* __restrict__ bias_sm, bool last, Release release) {
-  uint32_t ra[32], rb[32];
-  const uint32_t lane_base = (uint32_t)(q * 32) << 16;
-  ptx::tmem_ld_32x32(tmem_col0 + lane_base, ra);
-  ptx::tmem_ld_32x32(tmem_col0 + lane_base + 32, rb);
-  ptx::tmem_ld_wait();
-  if (last) release();
-#pragma unroll
-  for (int c = 0; c < 2; ++c) {
-    uint32_t (&cur)[32] = c ? rb : ra;
-    uint4* row = reinterpret_cast<uint4*>(my_stage + r_in_tile * GP_PITCH + c * 64);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {                   // four 16-byte chunks = 32 halves
-      const float4 b0 = *reinterpret_cast<const float4*>(bias_sm + 32 * c + 8 * j);
-      const float4 b1 = *reinterpret_cast<const float4*>(bias_sm + 32 * c + 8 * j + 4);
-      const __half2 h0 = __floats2half2_rn(__uint_as_float(cur[8 * j + 0]) + b0.x, __uint_as_float(cur[8 * j + 1]) + b0.y);
-      const __half2 h1 = __floats2half2_rn(__uint_as_float(cur[8 * j + 2]) + b0.z, __uint_as_float(cur[8 * j + 3]) + b0.w);
-      const __half2 h2 = __floats2half2_rn(__uint_as_float(cur[8 * j + 4]) + b1.x, __uint_as_float(cur[8 * j + 5]) + b1.y);
-      const __half2 h3 = __floats2half2_rn(__uint_as_float(cur[8 * j + 6]) + b1.z, __uint_as_float(cur[8 * j + 7]) + b1.w);
-      row[j] = make_uint4(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1),
-                          *reinterpret_cast<const uint32_t*>(&h2), *reinterpret_cast<const uint32_t*>(&h3));
-    }
-  }
-}
-
-// WRES = true (K <= 256: layer 0): weight-stationary pairs.  The number of pairs is a multiple of the number of
-// 256-column tiles, so a pair's column tile never changes: each CTA loads its 128 rows of W (all k-blocks, 64 KB at
-// K = 200) ONCE, and the ring carries only A (16 KB per stage, 7 stages).  The non-resident pair kernel at K = 200 was
-// bound by the ring, not by MMAs or HBM: 5 stages x 32 KB in flight against ~3.5 k cycles of load latency is one
-// 256 x 256 x 64 k-block per ~800 cycles, while its 4 (3.25 real) k-steps need 512; resident W halves the bytes per
-// k-block and leaves room for 7 stages -> 3.5x the k-blocks in flight.
 // 64 columns already in registers (two 32-column tcgen05.ld results) + bias -> row-major fp16 staging (GP_PITCH)
 __device__ __forceinline__ void f16_regs_to_stage(const uint32_t (&ra)[32], const uint32_t (&rb)[32], int r_in_tile,
                                                   unsigned char* my_stage, const float* __restrict__ bias_sm) {
