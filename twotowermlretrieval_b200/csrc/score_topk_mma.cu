@@ -26,6 +26,7 @@
 // cycles per round, 3 stages: 1850 cycles per tile); this is v4.
 #include <cudaTypedefs.h>
 
+#include <cstdlib>
 #include <type_traits>
 
 #include "common.cuh"
@@ -1376,12 +1377,15 @@ int launch_score_topk_mma(const float* Q, int B, const float* docs, int64_t N, i
     }
     attr_dev = cur_dev;
   }
-  // The survivor histogram pays where a CTA's own lists cannot tighten the bound fast enough: short scans (<= 640 tiles
-  // per CTA: 1/4 of the corpus and less at B <= 128) and CTA pairs (64-document tiles, twice the survivors per tile).
-  // Same-box A/B (r2): N = 1.1 M, B = 128: 0.248 -> 0.225 ms; N = 1 M, B = 256: 0.375 -> 0.256 ms; N = 8.84 M, B = 256:
-  // 2.05 -> 1.85 ms; but N = 8.84 M, B = 128 (1,867 tiles per CTA, lists fill by themselves): 1.326 -> 1.381 ms, so off there.
+  // The survivor histogram pays where a CTA's own lists cannot tighten the bound fast enough: short scans (<= 280 tiles
+  // per CTA: 1/8 of the corpus and less at B <= 128) and CTA pairs (64-document tiles, twice the survivors per tile).
+  // Same-box A/Bs (r2, B = 128, histogram off -> on): 0.8 M docs 0.210 -> 0.180 ms, 1.1 M 0.240 -> 0.229, 1.6 M 0.290 -> 0.301,
+  // 2.2 M 0.377 -> 0.397, 4.4 M 0.714 -> 0.719, 8.84 M 1.326 -> 1.381 (lists fill by themselves, the sweeps and REDs only
+  // cost); pairs: 1 M docs B = 256 0.375 -> 0.256, 8.84 M 2.05 -> 1.85.
   const int64_t scan_tiles_per_cta = ceil_div64(ceil_div64(N, (int64_t)p.nd_t), (int64_t)p.n_slices);
-  const bool use_hist = p.pair || scan_tiles_per_cta <= 640;
+  // (TTR_HIST_MAX_TILES overrides the 280 for the A/B, read once)
+  static const int64_t hist_max_tiles = [] { const char* e = getenv("TTR_HIST_MAX_TILES"); return e ? (int64_t)atoll(e) : (int64_t)280; }();
+  const bool use_hist = p.pair || scan_tiles_per_cta <= hist_max_tiles;
   if (!use_hist) hist = nullptr;
   FusedArgs fa{nullptr, nullptr, 0, hist, hpar};
   long long* tr = nullptr;
